@@ -1,0 +1,219 @@
+/*
+ * spkdiar.h - C-ABI of libspkdiar.so, the B200 (sm_100a) implementation of the
+ * statistical core of the Aalto speaker-diarization scripts.
+ *
+ * The reference (JianCao92/speaker-diarization) has NO plugin / FFI interface:
+ * its hot path is three Python-2 scripts whose numeric kernels are in-script
+ * functions calling numpy / scipy.  This header is therefore the boundary WE
+ * define; each entry point names the reference
+ * function(s) whose work it replaces.  The host side that binds it is
+ * speaker-diarization_b200/_abi.py (ctypes); INTEGRATION.md shows the stub a
+ * maintainer of the reference scripts would add.
+ *
+ * Conventions
+ *   - plain C types only; every call returns 0 on success or a negative
+ *     SPKDIAR_E_* code, with text from spkdiar_last_error();
+ *   - the caller owns every host buffer; the library owns device memory behind
+ *     opaque handles; handles belong to the context that made them;
+ *   - one context per (host thread, device); calls on one context are
+ *     serialised by the caller; every call is synchronous on return;
+ *   - frame positions are frame indices into the uploaded feature matrix,
+ *     half-open ranges [a, b); distances are IEEE fp64;
+ *   - there is no CPU fallback: without a usable sm_100-class device
+ *     spkdiar_create() fails.
+ */
+#ifndef SPKDIAR_H
+#define SPKDIAR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPKDIAR_ABI_VERSION 1
+
+/* error codes */
+#define SPKDIAR_OK            0
+#define SPKDIAR_E_CUDA       -1   /* a CUDA runtime call failed                     */
+#define SPKDIAR_E_ARG        -2   /* bad argument (null pointer, range, dimension)  */
+#define SPKDIAR_E_NOMEM      -3   /* host or device allocation failed               */
+#define SPKDIAR_E_CAPACITY   -4   /* caller-provided output buffer too small        */
+#define SPKDIAR_E_UNSUPPORTED -5  /* feature dimension / option not built           */
+#define SPKDIAR_E_NODEVICE   -6   /* no CUDA device / not an sm_100-class device    */
+
+/* distance measures: -d GLR|BIC|KL2 (spk-change-detection.py:428-435) */
+#define SPKDIAR_GLR 0
+#define SPKDIAR_BIC 1
+#define SPKDIAR_KL2 2
+
+/* the feature dimension the kernels are specialised for (fconfig.cfg:78-83) */
+#define SPKDIAR_DIM 39
+/* doubles per sufficient-statistics record: 780 packed second moments,
+ * 39 first moments, 1 frame count */
+#define SPKDIAR_RECORD 820
+
+typedef struct spkdiar_ctx  spkdiar_ctx;
+typedef struct spkdiar_feat spkdiar_feat;
+typedef struct spkdiar_clus spkdiar_clus;
+
+/* ---- context --------------------------------------------------------------- */
+
+int  spkdiar_abi_version(void);
+/* device: CUDA ordinal.  stream: a cudaStream_t the caller already owns (e.g.
+ * torch's current stream) passed as void*, or NULL to let the context create
+ * its own non-blocking stream. */
+int  spkdiar_create(int device, void* stream, spkdiar_ctx** out);
+void spkdiar_destroy(spkdiar_ctx* ctx);
+/* last error text of ctx (or of the failed spkdiar_create when ctx is NULL) */
+const char* spkdiar_last_error(const spkdiar_ctx* ctx);
+/* number of kernels the library launched on this context since creation */
+int64_t spkdiar_launch_count(const spkdiar_ctx* ctx);
+/* number of SMs of the context's device */
+int  spkdiar_sm_count(const spkdiar_ctx* ctx);
+
+/* Kernel-class timers (CUDA events on the context's stream).  enable != 0
+ * switches timing on and clears the accumulators.  spkdiar_profile_read fills
+ * ms[k] / launches[k] for k < SPKDIAR_NPROF. */
+#define SPKDIAR_PROF_STATS   0   /* frame-statistics prefix kernels (K1)            */
+#define SPKDIAR_PROF_SCORE   1   /* batched window / pair scoring (K2, K6)          */
+#define SPKDIAR_PROF_GW      2   /* persistent growing-window driver (K3)           */
+#define SPKDIAR_PROF_MERGE   3   /* persistent agglomerative merge loop (K7)        */
+#define SPKDIAR_PROF_H2D     4   /* host->device feature copies                     */
+#define SPKDIAR_NPROF        5
+int  spkdiar_profile_enable(spkdiar_ctx* ctx, int enable);
+int  spkdiar_profile_read(const spkdiar_ctx* ctx, double* ms, int64_t* launches);
+
+/* ---- features + frame statistics (K1) ---------------------------------------
+ * Replaces load_features' in-memory result (spk-change-detection.py:31-43) as
+ * the operand of every later np.cov / np.mean: the (n, dim) float32 frame-major
+ * matrix is copied to HBM and fp64 prefix sums of x and x x^T are built so that
+ * the covariance of any window is an O(dim^2) difference. */
+int  spkdiar_features_upload(spkdiar_ctx* ctx, const float* frames, int64_t n,
+                             int32_t dim, spkdiar_feat** out);
+/* same, for a matrix that already lives in device memory (not copied, must
+ * outlive the handle) */
+int  spkdiar_features_adopt(spkdiar_ctx* ctx, const float* dev_frames, int64_t n,
+                            int32_t dim, spkdiar_feat** out);
+/* (re)build the prefix statistics; upload/adopt already call it once */
+int  spkdiar_stats_build(spkdiar_feat* f);
+int  spkdiar_features_free(spkdiar_feat* f);
+int64_t spkdiar_features_frames(const spkdiar_feat* f);
+/* test hook: sufficient statistics of frames [a, b) in NATURAL order:
+ * out[0..38] = sum (x - shift), out[39 + i*(i+1)/2 + j] = sum (x-shift)_i (x-shift)_j
+ * (j <= i), shift[0..38] = the per-file shift the library subtracted */
+int  spkdiar_stats_window(spkdiar_feat* f, int64_t a, int64_t b, double* out819,
+                          double* shift39);
+
+/* ---- batched window scoring (K2) --------------------------------------------
+ * Replaces bic / glr / kl2 (spk-change-detection.py:72-133) for ncand
+ * candidates at once.  Candidate k splits [a[k], b[k]) at m[k]: left = [a, m),
+ * right = [m, b), pooled = [a, b).
+ *   out_d[k]        the distance (BIC uses lambda);
+ *   out_terms       NULL, or 3 doubles per candidate:
+ *                     BIC: ln|S_left|, ln|S_right|, ln|S_pooled|
+ *                     GLR: ln|S_left|, ln|S_right|, ln|(N1/N) S1 + (N2/N) S2|
+ *                     KL2: first trace term, second trace term, 0
+ *                   (the host needs the terms to replay the reference's
+ *                    mutable-default BIC memo, spk-change-detection.py:72,84-90)
+ */
+int  spkdiar_score_windows(spkdiar_feat* f, const int64_t* a, const int64_t* m,
+                           const int64_t* b, int64_t ncand, int metric,
+                           double lambda, double* out_d, double* out_terms);
+
+/* Distance between two SETS of frame ranges (clusters): set 1 = ranges
+ * [a1[i], b1[i]) i < n1, set 2 likewise; pooled = concatenation.  Replaces one
+ * dist(arr1, arr2) call of spk-clustering.py:136-175 (in-order clustering) and
+ * of merge_rec (spk-change-detection.py:136-177).  npairs problems are scored
+ * at once: problem p uses ranges off1[p]..off1[p+1] of (a1, b1) and
+ * off2[p]..off2[p+1] of (a2, b2). */
+int  spkdiar_score_sets(spkdiar_feat* f, int64_t npairs,
+                        const int64_t* off1, const int64_t* a1, const int64_t* b1,
+                        const int64_t* off2, const int64_t* a2, const int64_t* b2,
+                        int metric, double lambda,
+                        double* out_d, double* out_terms);
+
+/* ---- growing-window search (K3) ---------------------------------------------
+ * Replaces dist_gw (spk-change-detection.py:180-288): the whole sequential
+ * search (coarse scan, threshold test, fine tune, reset-at-change, window
+ * growth) runs on the device, one independent chain per recipe line. */
+typedef struct {
+    double rate;        /* float(-f)                                   CD:499 */
+    double winsize;     /* floor(-w * rate)      frames                CD:526 */
+    double winstep;     /* floor(-st * rate)     frames                CD:527 */
+    double deltaws;     /* floor(rate * -dws)    frames                CD:508 */
+    double threshold;   /* -t                                          CD:532 */
+    double lambda;      /* -l (BIC only)                               CD:455 */
+    int32_t metric;     /* SPKDIAR_GLR | _BIC | _KL2                          */
+    int32_t max_groups; /* 0 = automatic; else cap on concurrently running
+                           chains (1 = the whole GPU works on one chain)      */
+} spkdiar_gw_params;
+
+/* one record per window the reference's outer loop visits (CD:201) */
+typedef struct {
+    double  start;      /* window start, chain-relative, fp64 as the reference */
+    double  end;        /* window end                                          */
+    double  maxi;       /* best coarse offset i                                */
+    double  maxd;       /* best coarse distance; -2^63 when no candidate won   */
+    double  maxi_fine;  /* after the fine tune (positive windows only)         */
+    double  maxd_fine;
+    int32_t positive;   /* 1: a change was written at start + maxi_fine        */
+    int32_t chain;      /* index of the recipe line / chain                    */
+    int32_t ncand;      /* coarse candidates evaluated; when none of them won
+                           (all NaN / inf / no candidate) encoded as -(n + 1)  */
+    int32_t ninf;       /* candidates (coarse + fine) whose distance was +-inf */
+    int32_t seq;        /* position of the window within its chain             */
+    int32_t pad;
+} spkdiar_gw_window;
+
+/* chains: chain c covers frames [seg_a[c], seg_b[c]) of f.  Window records are
+ * returned chain by chain, in window order; win_first[c]..win_first[c+1]
+ * (nchain + 1 entries) index chain c's records.  A too small win_cap returns
+ * SPKDIAR_E_CAPACITY and stores the needed count in win_first[0]. */
+int  spkdiar_gw_run(spkdiar_feat* f, const spkdiar_gw_params* params,
+                    const int64_t* seg_a, const int64_t* seg_b, int32_t nchain,
+                    spkdiar_gw_window* win, int64_t win_cap, int64_t* win_first);
+
+/* ---- agglomerative clustering (K5-K7) ---------------------------------------
+ * Replaces spk_cluster_hi of spk-clustering.py:178-260 (variant 1) and of
+ * spk-clustering2.py:173-229 (variant 2).  Initial clusters are the frame
+ * ranges [seg_a[k], seg_b[k]).  The device keeps per-cluster sufficient
+ * statistics and the pair matrix resident and runs the merge loop without a
+ * host round trip. */
+typedef struct {
+    int32_t a;          /* surviving cluster, index in the compacted list      */
+    int32_t b;          /* removed cluster (a < b), same indexing              */
+    double  d;          /* the minimum that triggered the merge                */
+} spkdiar_merge;
+
+/* stats[0..3] = max_dist, min_dist, max_det_dist, min_det_dist as the scripts
+ * track them (variant 1: over every finite distance ever computed,
+ * spk-clustering.py:196-200,233-237,210-213; variant 2: matrix max / min at
+ * convergence, spk-clustering2.py:220-221), starting from 0 / 2^63-1. */
+int  spkdiar_cluster_create(spkdiar_feat* f, const int64_t* seg_a,
+                            const int64_t* seg_b, int64_t nseg, int metric,
+                            double lambda, spkdiar_clus** out);
+int  spkdiar_cluster_run(spkdiar_clus* c, double threshold, int32_t max_spk,
+                         int32_t variant, spkdiar_merge* out, int64_t cap,
+                         int64_t* nmerges, double* stats4);
+/* row-sharded run for one very long recording (BASELINE config 5): this rank
+ * owns the pair-matrix rows r with r % nranks == rank.  exchange() is called
+ * once per merge with this rank's best candidate (16 bytes: fp64 distance,
+ * int64 flat index) and must fill all[nranks] with every rank's candidate
+ * (an all-gather; the host supplies it so that the library does not link
+ * NCCL/MPI itself). */
+typedef int (*spkdiar_exchange_fn)(void* user, const void* mine16, void* all);
+int  spkdiar_cluster_run_sharded(spkdiar_clus* c, double threshold,
+                                 int32_t max_spk, int32_t rank, int32_t nranks,
+                                 spkdiar_exchange_fn exchange, void* user,
+                                 spkdiar_merge* out, int64_t cap,
+                                 int64_t* nmerges, double* stats4);
+int  spkdiar_cluster_free(spkdiar_clus* c);
+/* test hook: copy the current pair matrix (nseg x nseg, row-major, entries of
+ * dead rows / columns undefined) and the alive flags to the host */
+int  spkdiar_cluster_matrix(spkdiar_clus* c, double* out, uint8_t* alive);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPKDIAR_H */

@@ -1,0 +1,334 @@
+"""ctypes binding of ``libspkdiar.so`` (the C-ABI of ``include/spkdiar.h``).
+
+Thin by design: argument marshalling (numpy arrays -> pointers), error codes ->
+``SpkdiarError``, handle lifetime.  No numeric work happens here and there is
+no fallback: if the library is not built, or no sm_100-class GPU is present,
+every entry point raises.
+"""
+
+import ctypes as C
+import os
+import os.path as op
+
+import numpy as np
+
+GLR, BIC, KL2 = 0, 1, 2
+METRIC = {'GLR': GLR, 'BIC': BIC, 'KL2': KL2}
+DIM = 39
+RECORD = 820
+NPROF = 5
+PROF_NAMES = ('stats', 'score', 'gw', 'merge', 'h2d')
+
+LIB_PATH = op.join(op.dirname(op.abspath(__file__)), 'csrc', 'libspkdiar.so')
+
+# every symbol include/spkdiar.h declares (tests check the library exports them)
+SYMBOLS = (
+    'spkdiar_abi_version', 'spkdiar_create', 'spkdiar_destroy', 'spkdiar_last_error',
+    'spkdiar_launch_count', 'spkdiar_sm_count', 'spkdiar_profile_enable',
+    'spkdiar_profile_read', 'spkdiar_features_upload', 'spkdiar_features_adopt',
+    'spkdiar_stats_build', 'spkdiar_features_free', 'spkdiar_features_frames',
+    'spkdiar_stats_window', 'spkdiar_score_windows', 'spkdiar_score_sets',
+    'spkdiar_gw_run', 'spkdiar_cluster_create', 'spkdiar_cluster_run',
+    'spkdiar_cluster_run_sharded', 'spkdiar_cluster_free', 'spkdiar_cluster_matrix',
+)
+
+
+class SpkdiarError(RuntimeError):
+    def __init__(self, code, text):
+        RuntimeError.__init__(self, 'libspkdiar error %d: %s' % (code, text))
+        self.code = code
+
+
+class GwParams(C.Structure):
+    _fields_ = [('rate', C.c_double), ('winsize', C.c_double), ('winstep', C.c_double),
+                ('deltaws', C.c_double), ('threshold', C.c_double), ('lambda_', C.c_double),
+                ('metric', C.c_int32), ('max_groups', C.c_int32)]
+
+
+GW_WINDOW_DTYPE = np.dtype([('start', '<f8'), ('end', '<f8'), ('maxi', '<f8'), ('maxd', '<f8'),
+                            ('maxi_fine', '<f8'), ('maxd_fine', '<f8'), ('positive', '<i4'),
+                            ('chain', '<i4'), ('ncand', '<i4'), ('ninf', '<i4'), ('seq', '<i4'),
+                            ('pad', '<i4')])
+MERGE_DTYPE = np.dtype([('a', '<i4'), ('b', '<i4'), ('d', '<f8')])
+assert GW_WINDOW_DTYPE.itemsize == 72 and MERGE_DTYPE.itemsize == 16
+
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+
+_lib = None
+
+
+def _p(arr, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def load_library(path=None):
+    """dlopen the library and declare its prototypes.  Raises ``SpkdiarError``
+    when it has not been built (``python -c 'import __graft_entry__ as g;
+    g.build()'``)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or os.environ.get('SPKDIAR_LIB', LIB_PATH)
+    if not op.isfile(path):
+        raise SpkdiarError(-6, 'libspkdiar.so not found at %s - build it first '
+                           '(__graft_entry__.build()); there is no CPU fallback' % path)
+    lib = C.CDLL(path)
+    vp, i64, i32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_double
+    pi64, pdbl = C.POINTER(C.c_int64), C.POINTER(C.c_double)
+    proto = {
+        'spkdiar_abi_version': (C.c_int, []),
+        'spkdiar_create': (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
+        'spkdiar_destroy': (None, [vp]),
+        'spkdiar_last_error': (C.c_char_p, [vp]),
+        'spkdiar_launch_count': (i64, [vp]),
+        'spkdiar_sm_count': (C.c_int, [vp]),
+        'spkdiar_profile_enable': (C.c_int, [vp, C.c_int]),
+        'spkdiar_profile_read': (C.c_int, [vp, pdbl, pi64]),
+        'spkdiar_features_upload': (C.c_int, [vp, vp, i64, i32, C.POINTER(vp)]),
+        'spkdiar_features_adopt': (C.c_int, [vp, vp, i64, i32, C.POINTER(vp)]),
+        'spkdiar_stats_build': (C.c_int, [vp]),
+        'spkdiar_features_free': (C.c_int, [vp]),
+        'spkdiar_features_frames': (i64, [vp]),
+        'spkdiar_stats_window': (C.c_int, [vp, i64, i64, pdbl, pdbl]),
+        'spkdiar_score_windows': (C.c_int, [vp, pi64, pi64, pi64, i64, C.c_int, dbl, pdbl, pdbl]),
+        'spkdiar_score_sets': (C.c_int, [vp, i64, pi64, pi64, pi64, pi64, pi64, pi64, C.c_int, dbl,
+                                         pdbl, pdbl]),
+        'spkdiar_gw_run': (C.c_int, [vp, C.POINTER(GwParams), pi64, pi64, i32, vp, i64, pi64]),
+        'spkdiar_cluster_create': (C.c_int, [vp, pi64, pi64, i64, C.c_int, dbl, C.POINTER(vp)]),
+        'spkdiar_cluster_run': (C.c_int, [vp, dbl, i32, i32, vp, i64, pi64, pdbl]),
+        'spkdiar_cluster_run_sharded': (C.c_int, [vp, dbl, i32, i32, i32, EXCHANGE_FN, vp, vp, i64,
+                                                  pi64, pdbl]),
+        'spkdiar_cluster_free': (C.c_int, [vp]),
+        'spkdiar_cluster_matrix': (C.c_int, [vp, pdbl, C.POINTER(C.c_uint8)]),
+    }
+    for name, (res, args) in proto.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.spkdiar_abi_version() != 1:
+        raise SpkdiarError(-5, 'ABI version mismatch: %d' % lib.spkdiar_abi_version())
+    if path == os.environ.get('SPKDIAR_LIB', LIB_PATH):
+        _lib = lib
+    return lib
+
+
+class Context(object):
+    """One device context (``spkdiar_ctx``).  ``stream``: an existing
+    ``cudaStream_t`` as an int (e.g. ``torch.cuda.current_stream().cuda_stream``)
+    or None."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.spkdiar_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise SpkdiarError(rc, (self.lib.spkdiar_last_error(None) or b'').decode())
+        self.h = h
+        self.device = int(device)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SpkdiarError(rc, (self.lib.spkdiar_last_error(self.h) or b'').decode())
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.spkdiar_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def launches(self):
+        return int(self.lib.spkdiar_launch_count(self.h))
+
+    @property
+    def sm_count(self):
+        return int(self.lib.spkdiar_sm_count(self.h))
+
+    def profile(self, enable=True):
+        self._check(self.lib.spkdiar_profile_enable(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> {class: (ms, launches)}"""
+        ms = np.zeros(NPROF)
+        n = np.zeros(NPROF, dtype=np.int64)
+        self._check(self.lib.spkdiar_profile_read(self.h, _p(ms, C.c_double), _p(n, C.c_int64)))
+        return {PROF_NAMES[k]: (float(ms[k]), int(n[k])) for k in range(NPROF)}
+
+    def upload(self, frames):
+        """(n, 39) float32 host matrix -> Features (copied to HBM, statistics built)."""
+        frames = np.ascontiguousarray(frames, dtype=np.float32)
+        if frames.ndim != 2:
+            raise ValueError('frames must be (n, dim)')
+        h = C.c_void_p()
+        self._check(self.lib.spkdiar_features_upload(self.h, frames.ctypes.data_as(C.c_void_p),
+                                                     frames.shape[0], frames.shape[1], C.byref(h)))
+        return Features(self, h, frames.shape[0])
+
+    def upload_ptr(self, host_ptr, n, dim=DIM):
+        """Same from a raw host pointer (e.g. pinned torch memory)."""
+        h = C.c_void_p()
+        self._check(self.lib.spkdiar_features_upload(self.h, C.c_void_p(host_ptr), n, dim, C.byref(h)))
+        return Features(self, h, n)
+
+    def adopt(self, dev_ptr, n, dim=DIM):
+        """Features over a matrix already in device memory (not copied)."""
+        h = C.c_void_p()
+        self._check(self.lib.spkdiar_features_adopt(self.h, C.c_void_p(dev_ptr), n, dim, C.byref(h)))
+        return Features(self, h, n)
+
+
+class Features(object):
+    """``spkdiar_feat``: frames + prefix statistics resident in HBM."""
+
+    def __init__(self, ctx, handle, n):
+        self.ctx = ctx
+        self.h = handle
+        self.n = int(n)
+
+    def close(self):
+        if getattr(self, 'h', None) and self.ctx.h:
+            self.ctx.lib.spkdiar_features_free(self.h)
+        self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def rebuild_stats(self):
+        self.ctx._check(self.ctx.lib.spkdiar_stats_build(self.h))
+
+    def stats_window(self, a, b):
+        """-> (sum[39], packed lower-triangular second moments [780], shift[39])"""
+        out = np.zeros(819)
+        shift = np.zeros(39)
+        self.ctx._check(self.ctx.lib.spkdiar_stats_window(self.h, int(a), int(b), _p(out, C.c_double),
+                                                          _p(shift, C.c_double)))
+        return out[:39], out[39:], shift
+
+    def score_windows(self, a, m, b, metric, lambdac=1.3, terms=False):
+        a, m, b = _i64(a), _i64(m), _i64(b)
+        n = a.shape[0]
+        d = np.empty(n)
+        t = np.empty((n, 3)) if terms else None
+        self.ctx._check(self.ctx.lib.spkdiar_score_windows(
+            self.h, _p(a, C.c_int64), _p(m, C.c_int64), _p(b, C.c_int64), n, int(metric),
+            float(lambdac), _p(d, C.c_double), _p(t, C.c_double) if terms else None))
+        return (d, t) if terms else d
+
+    def score_sets(self, sets1, sets2, metric, lambdac=1.3, terms=False):
+        """sets1[p], sets2[p]: lists of (a, b) frame ranges; one distance per p."""
+        def pack(sets):
+            off = np.zeros(len(sets) + 1, dtype=np.int64)
+            for k, s in enumerate(sets):
+                off[k + 1] = off[k] + len(s)
+            flat = [r for s in sets for r in s]
+            ra = np.array([r[0] for r in flat], dtype=np.int64)
+            rb = np.array([r[1] for r in flat], dtype=np.int64)
+            return off, ra, rb
+        n = len(sets1)
+        assert len(sets2) == n
+        o1, a1, b1 = pack(sets1)
+        o2, a2, b2 = pack(sets2)
+        d = np.empty(n)
+        t = np.empty((n, 3)) if terms else None
+        self.ctx._check(self.ctx.lib.spkdiar_score_sets(
+            self.h, n, _p(o1, C.c_int64), _p(a1, C.c_int64), _p(b1, C.c_int64),
+            _p(o2, C.c_int64), _p(a2, C.c_int64), _p(b2, C.c_int64), int(metric), float(lambdac),
+            _p(d, C.c_double), _p(t, C.c_double) if terms else None))
+        return (d, t) if terms else d
+
+    def gw_run(self, seg_a, seg_b, rate, winsize, winstep, deltaws, threshold, lambdac, metric,
+               max_groups=0, cap=None):
+        """-> (window records [structured array], win_first [nchain + 1])"""
+        seg_a, seg_b = _i64(seg_a), _i64(seg_b)
+        nchain = seg_a.shape[0]
+        prm = GwParams(float(rate), float(winsize), float(winstep), float(deltaws), float(threshold),
+                       float(lambdac), int(metric), int(max_groups))
+        if cap is None:
+            unit = max(float(rate) / 2 - float(rate) / 10, 1.0)
+            cap = int(sum(2 * ((b - a) / unit + 2) for a, b in zip(seg_a, seg_b))) + 16
+        first = np.zeros(nchain + 1, dtype=np.int64)
+        while True:
+            win = np.zeros(cap, dtype=GW_WINDOW_DTYPE)
+            rc = self.ctx.lib.spkdiar_gw_run(self.h, C.byref(prm), _p(seg_a, C.c_int64), _p(seg_b, C.c_int64),
+                                             nchain, win.ctypes.data_as(C.c_void_p), cap, _p(first, C.c_int64))
+            if rc == -4 and first[0] > cap:            # SPKDIAR_E_CAPACITY: retry with the needed size
+                cap = int(first[0])
+                continue
+            self.ctx._check(rc)
+            return win[:int(first[nchain])], first
+
+    def cluster(self, seg_a, seg_b, metric, lambdac=1.3):
+        seg_a, seg_b = _i64(seg_a), _i64(seg_b)
+        h = C.c_void_p()
+        self.ctx._check(self.ctx.lib.spkdiar_cluster_create(
+            self.h, _p(seg_a, C.c_int64), _p(seg_b, C.c_int64), seg_a.shape[0], int(metric),
+            float(lambdac), C.byref(h)))
+        return Clusters(self, h, seg_a.shape[0])
+
+
+class Clusters(object):
+    """``spkdiar_clus``: per-cluster statistics + pair matrix resident in HBM."""
+
+    def __init__(self, feat, handle, n):
+        self.feat = feat
+        self.ctx = feat.ctx
+        self.h = handle
+        self.n = int(n)
+
+    def close(self):
+        if getattr(self, 'h', None) and self.ctx.h:
+            self.ctx.lib.spkdiar_cluster_free(self.h)
+        self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def run(self, threshold, max_spk=0, variant=1):
+        """-> (merges [structured array of (a, b, d), compacted indices], stats[4])"""
+        out = np.zeros(max(self.n, 1), dtype=MERGE_DTYPE)
+        nm = C.c_int64(0)
+        stats = np.zeros(4)
+        self.ctx._check(self.ctx.lib.spkdiar_cluster_run(
+            self.h, float(threshold), int(max_spk), int(variant), out.ctypes.data_as(C.c_void_p),
+            out.shape[0], C.byref(nm), _p(stats, C.c_double)))
+        return out[:nm.value], stats
+
+    def run_sharded(self, threshold, max_spk, rank, nranks, exchange):
+        """``exchange(mine: bytes) -> bytes`` is an all-gather of 16-byte candidates."""
+        out = np.zeros(max(self.n, 1), dtype=MERGE_DTYPE)
+        nm = C.c_int64(0)
+        stats = np.zeros(4)
+
+        def _cb(user, mine, allp):
+            try:
+                got = exchange(C.string_at(mine, 16))
+                C.memmove(allp, got, 16 * nranks)
+                return 0
+            except Exception:           # pragma: no cover - surfaced as an error code
+                return -1
+        cb = EXCHANGE_FN(_cb)
+        self.ctx._check(self.ctx.lib.spkdiar_cluster_run_sharded(
+            self.h, float(threshold), int(max_spk), int(rank), int(nranks), cb, None,
+            out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(nm), _p(stats, C.c_double)))
+        return out[:nm.value], stats
+
+    def matrix(self):
+        m = np.empty((self.n, self.n))
+        alive = np.empty(self.n, dtype=np.uint8)
+        self.ctx._check(self.ctx.lib.spkdiar_cluster_matrix(self.h, _p(m, C.c_double), _p(alive, C.c_uint8)))
+        return m, alive.astype(bool)

@@ -1,0 +1,329 @@
+// cluster.cuh - K5-K7: the agglomerative clustering engine.
+//
+// Replaces spk_cluster_hi of spk-clustering.py:178-260 (variant 1) and
+// spk-clustering2.py:173-229 (variant 2).  The reference re-concatenates the raw
+// frames of both clusters and runs np.cov for every pair it scores; here every
+// cluster is one 820-double sufficient-statistics record resident in HBM
+// (pooled statistics of two clusters = the sum of their records), the pair
+// matrix stays on the device, and the merge loop is ONE persistent cooperative
+// kernel: per merge a grid-wide exact argmin (NaN-first, first flat index wins,
+// as ndarray.min()/argmin() behave - SURVEY.md Q8), the stop test, and the
+// rescoring of the merged row (and column in variant 1), separated by two grid
+// barriers.  Variant 2 keeps the reference's stale entries (Q5): the matrix is
+// the full N x N array, only row `a` is rewritten after a merge.
+//
+// Indices inside the kernel are ORIGINAL cluster indices with an alive mask;
+// deleting row/column b in the reference preserves order, so the flat-index
+// tie-break is the same.  The host wrapper converts to compacted indices.
+#pragma once
+
+#include "common.cuh"
+#include "score.cuh"
+
+struct spkdiar_clus {
+    spkdiar_ctx* ctx = nullptr;
+    spkdiar_feat* feat = nullptr;
+    int64_t n = 0;               // initial clusters
+    int metric = SPKDIAR_BIC;
+    double lambda = 1.3;
+    int64_t* seg = nullptr;      // device: a[n], b[n]
+    double* rec = nullptr;       // [n][REC]
+    double* ld = nullptr;        // [n] ln|S_i|
+    double* M = nullptr;         // [n][n]
+    uint8_t* alive = nullptr;    // [n] (final state, for the test hook)
+    bool ran = false;
+};
+
+namespace spk {
+
+constexpr int CL_WARPS = 8;
+constexpr int CL_THREADS = CL_WARPS * 32;
+#define CL_MAXINT_D 9223372036854775807.0      /* float(sys.maxint) == 2^63 */
+
+struct ClBest { double v; int64_t idx; };
+
+// "a comes before b" under ndarray.argmin(): NaN first, then smaller value, then smaller flat index
+__device__ __forceinline__ bool cl_before(double av, int64_t ai, double bv, int64_t bi) {
+    const bool an = av != av, bn = bv != bv;
+    if (an || bn) return an && (!bn || ai < bi);
+    return av < bv || (av == bv && ai < bi);
+}
+__device__ __forceinline__ void cl_take(ClBest& x, double v, int64_t i) {
+    if (cl_before(v, i, x.v, x.idx)) { x.v = v; x.idx = i; }
+}
+__device__ __forceinline__ ClBest cl_warp_best(ClBest x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, x.v, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, (long long)x.idx, o);
+        cl_take(x, ov, oi);
+    }
+    return x;
+}
+
+// order-preserving map double -> uint64 for atomicMax / atomicMin
+__device__ __forceinline__ unsigned long long cl_ord(double d) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+inline double cl_unord(unsigned long long k) {
+    const unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+    double d;
+    memcpy(&d, &u, sizeof(d));
+    return d;
+}
+__device__ __forceinline__ void cl_track(double d, unsigned long long* stat) {   // stat[0]=max, stat[1]=min over finite d
+    if (d == d_inf() || d == -d_inf() || d != d) return;    // `d > max` / `d < min` are false for NaN
+    atomicMax(stat + 0, cl_ord(d));
+    atomicMin(stat + 1, cl_ord(d));
+}
+
+__global__ void __launch_bounds__(256)
+cl_init_records(const double* __restrict__ P, const int64_t* __restrict__ seg, int64_t n,
+                double* __restrict__ rec) {
+    const int64_t s = blockIdx.x;
+    const double* pa = P + seg[s] * REC;
+    const double* pb = P + seg[n + s] * REC;
+    for (int q = threadIdx.x; q < REC; q += blockDim.x) rec[s * REC + q] = __ldg(pb + q) - __ldg(pa + q);
+}
+
+__global__ void __launch_bounds__(SC_THREADS, 3)
+cl_self_logdet(const double* rec, int64_t n, double* __restrict__ ld) {
+    __shared__ __align__(16) WarpScratch ws[SC_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t i = (int64_t)blockIdx.x * SC_WARPS + warp; i < n; i += (int64_t)gridDim.x * SC_WARPS) {
+        const RecSrc X{rec + i * REC};
+        const double v = logdet_term(0, SPKDIAR_BIC, X, X, ws[warp], lane);
+        if (lane == 0) ld[i] = v;
+    }
+}
+
+__global__ void cl_fill_const(double* __restrict__ M, int64_t n, double offdiag, double diag) {
+    const int64_t total = n * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n, c = i - r * n;
+        M[i] = r == c ? diag : offdiag;
+    }
+}
+
+// pair p of the strict upper triangle, row-major -> (i, j)
+__device__ __forceinline__ void cl_pair(int64_t p, int64_t n, int64_t& i, int64_t& j) {
+    const double b = 2.0 * (double)n - 1.0;
+    int64_t r = (int64_t)((b - sqrt(b * b - 8.0 * (double)p)) * 0.5);
+    if (r < 0) r = 0;
+    if (r > n - 2) r = n - 2;
+    // first pair of row r is r*n - r*(r+1)/2
+    while (r > 0 && r * n - (r * (r + 1)) / 2 > p) --r;
+    while ((r + 1) * n - ((r + 1) * (r + 2)) / 2 <= p) ++r;
+    i = r;
+    j = p - (r * n - (r * (r + 1)) / 2) + r + 1;
+}
+
+// distance of clusters X (arr1) and Y (arr2) from their records and cached ln|S|
+template <class SrcX, class SrcY>
+__device__ __forceinline__ double cl_pair_distance(int metric, double lambda, const SrcX& X, const SrcY& Y,
+                                                   double ldx, double ldy, WarpScratch& w, int lane) {
+    const double t = logdet_term(2, metric, X, Y, w, lane);
+    const double N1 = X(L39::CNT), N2 = Y(L39::CNT);
+    return metric == SPKDIAR_BIC ? bic_combine(N1, N2, ldx, ldy, t, lambda)
+                                 : glr_combine(N1, N2, ldx, ldy, t);
+}
+
+// initial fill, spk-clustering.py:188-200 / spk-clustering2.py:180-184
+__global__ void __launch_bounds__(SC_THREADS, 3)
+cl_fill_pairs(const double* rec, const double* __restrict__ ld, int64_t n, int metric, double lambda,
+              int variant, double* __restrict__ M, unsigned long long* stat) {
+    __shared__ __align__(16) WarpScratch ws[SC_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t npair = (n * (n - 1)) / 2;
+    for (int64_t p = (int64_t)blockIdx.x * SC_WARPS + warp; p < npair; p += (int64_t)gridDim.x * SC_WARPS) {
+        int64_t i, j;
+        cl_pair(p, n, i, j);
+        const RecSrc X{rec + i * REC}, Y{rec + j * REC};
+        const double d = cl_pair_distance(metric, lambda, X, Y, ld[i], ld[j], ws[warp], lane);
+        if (lane == 0) {
+            M[i * n + j] = d;
+            if (variant == 1) { M[j * n + i] = d; cl_track(d, stat); }
+        }
+    }
+}
+
+struct ClDev {
+    double* rec; double* ld; double* M; uint8_t* alive_out;
+    int64_t n;
+    int metric; double lambda; double threshold; int max_spk; int variant;
+    ClBest* slots;               // [grid] per-CTA candidates, double-buffered by merge parity: [2][grid]
+    unsigned long long* bar;
+    unsigned long long* stat;    // [0]=max [1]=min (ordered keys) over finite distances; [2]=max_det [3]=min_det
+    spkdiar_merge* out; int64_t cap;
+    long long* nmerge;           // merges performed
+    double* final_min;           // the minimum that stopped the loop
+};
+
+__device__ __forceinline__ void cl_grid_barrier(unsigned long long* ctr, unsigned long long& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += (unsigned long long)gridDim.x;
+        __threadfence();
+        atomicAdd(ctr, 1ULL);
+        while (*((volatile unsigned long long*)ctr) < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// shared memory: alive bitmask [ceil(n/32)] words, merged record [REC], per-warp scratch
+__global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
+    extern __shared__ __align__(16) unsigned char cl_smem[];
+    WarpScratch* ws = reinterpret_cast<WarpScratch*>(cl_smem);
+    double* merged = reinterpret_cast<double*>(cl_smem + CL_WARPS * sizeof(WarpScratch));
+    ClBest* wbest = reinterpret_cast<ClBest*>(merged + REC);
+    double* shd = reinterpret_cast<double*>(wbest + CL_WARPS);      // [0] ld_ab
+    uint32_t* abits = reinterpret_cast<uint32_t*>(shd + 2);
+    __shared__ ClBest gbest;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t n = g.n;
+    const int64_t gwarp = (int64_t)blockIdx.x * CL_WARPS + warp;
+    const int64_t nwarps = (int64_t)gridDim.x * CL_WARPS;
+    const int nwords = (int)((n + 31) / 32);
+    for (int wd = threadIdx.x; wd < nwords; wd += CL_THREADS) {
+        const int64_t lo = (int64_t)wd * 32;
+        abits[wd] = (n - lo >= 32) ? 0xffffffffu : ((1u << (int)(n - lo)) - 1u);
+    }
+    __syncthreads();
+    unsigned long long bar_target = 0;
+    int64_t nalive = n;
+    long long nm = 0;
+    double det_max = 0.0, det_min = CL_MAXINT_D;           // spk-clustering.py:418-419
+
+    for (;;) {
+        // ---------- SCAN: exact argmin over the alive part of the matrix ----------
+        ClBest mine{d_inf(), INT64_MAX};
+        for (int64_t r = gwarp; r < n; r += nwarps) {
+            if (!((abits[r >> 5] >> (r & 31)) & 1u)) continue;
+            const double* row = g.M + r * n;
+            for (int64_t c0 = 0; c0 < n; c0 += 32) {
+                const uint32_t word = abits[c0 >> 5];
+                const int64_t c = c0 + lane;
+                if ((word >> lane) & 1u) cl_take(mine, __ldcg(row + c), r * n + c);
+            }
+        }
+        mine = cl_warp_best(mine);
+        if (lane == 0) wbest[warp] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ClBest b = wbest[0];
+            for (int w = 1; w < CL_WARPS; ++w) cl_take(b, wbest[w].v, wbest[w].idx);
+            g.slots[(nm & 1) * gridDim.x + blockIdx.x] = b;
+        }
+        cl_grid_barrier(g.bar, bar_target);
+        if (warp == 0) {
+            ClBest b{d_inf(), INT64_MAX};
+            const ClBest* sl = g.slots + (nm & 1) * gridDim.x;
+            for (int s = lane; s < (int)gridDim.x; s += 32) {
+                const double v = __ldcg(&sl[s].v);
+                const long long i = __ldcg((const long long*)&sl[s].idx);
+                cl_take(b, v, i);
+            }
+            b = cl_warp_best(b);
+            if (lane == 0) gbest = b;
+        }
+        __syncthreads();
+        const double mind = gbest.v;
+        const int64_t bi = gbest.idx / n, bj = gbest.idx - (gbest.idx / n) * n;
+        const int64_t a = bi < bj ? bi : bj, b = bi < bj ? bj : bi;
+        // ---------- stop test, spk-clustering.py:207-208 ----------
+        const bool go = (mind <= g.threshold) || (g.max_spk > 0 && nalive > (int64_t)g.max_spk);
+        if (!go || a == b) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                *g.nmerge = nm;
+                *g.final_min = mind;
+                g.stat[2] = (unsigned long long)__double_as_longlong(det_max);
+                g.stat[3] = (unsigned long long)__double_as_longlong(det_min);
+            }
+            break;
+        }
+        if (mind > det_max) det_max = mind;                 // spk-clustering.py:210-213
+        if (mind < det_min) det_min = mind;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && nm < g.cap) {
+            spkdiar_merge mr; mr.a = (int32_t)a; mr.b = (int32_t)b; mr.d = mind;
+            g.out[nm] = mr;
+        }
+        // ---------- MERGE + RESCORE ----------
+        for (int q = threadIdx.x; q < REC; q += CL_THREADS)
+            merged[q] = __ldcg(g.rec + a * REC + q) + __ldcg(g.rec + b * REC + q);
+        if (threadIdx.x == 0) abits[b >> 5] &= ~(1u << (b & 31));
+        __syncthreads();
+        const SmemSrc X{merged};
+        // Round 0: warp 0 of every CTA computes ln|S_ab| (redundantly across CTAs) while the
+        // other warps already factorise their first pooled matrix; one __syncthreads later
+        // everybody knows ln|S_ab|.  One call site of the factorisation for all of it.
+        auto next_k = [&](int64_t from) {
+            while (from < n && (from == a || !((abits[from >> 5] >> (from & 31)) & 1u))) from += nwarps;
+            return from;
+        };
+        int64_t k = next_k(gwarp);
+        const double N1 = merged[L39::CNT];
+        double ld_ab = 0.0;
+        for (int round = 0;; ++round) {
+            bool has; int term; int64_t kk;
+            if (round == 0 && warp == 0) { has = true; term = 0; kk = a; }
+            else { has = k < n; term = 2; kk = has ? k : a; if (has) k = next_k(k + nwarps); }
+            if (!has && round > 0) break;
+            double t = 0.0;
+            if (has) {
+                const RecSrc Y{g.rec + kk * REC};
+                t = logdet_term(term, g.metric, X, Y, ws[warp], lane);
+            }
+            if (round == 0) {
+                if (warp == 0 && lane == 0) shd[0] = t;
+                __syncthreads();
+                ld_ab = shd[0];
+            }
+            if (has && term == 2 && lane == 0) {
+                const double N2 = __ldcg(g.rec + kk * REC + L39::CNT);
+                const double ldk = __ldcg(g.ld + kk);
+                const double d = g.metric == SPKDIAR_BIC ? bic_combine(N1, N2, ld_ab, ldk, t, g.lambda)
+                                                         : glr_combine(N1, N2, ld_ab, ldk, t);
+                g.M[a * n + kk] = d;                                            // row a
+                if (g.variant == 1) { g.M[kk * n + a] = d; cl_track(d, g.stat); }   // and column a
+            }
+        }
+        cl_grid_barrier(g.bar, bar_target);
+        // ---------- commit (CTA 0): the merged record replaces a's ----------
+        if (blockIdx.x == 0) {
+            for (int q = threadIdx.x; q < REC; q += CL_THREADS) g.rec[a * REC + q] = merged[q];
+            if (threadIdx.x == 0) g.ld[a] = ld_ab;
+        }
+        --nalive;
+        ++nm;
+    }
+    if (blockIdx.x == 0) {
+        __syncthreads();
+        for (int64_t i = threadIdx.x; i < n; i += CL_THREADS) g.alive_out[i] = (abits[i >> 5] >> (i & 31)) & 1u;
+    }
+}
+
+// spk-clustering2.py:220: distances.max() over the compacted matrix (NaN propagates)
+__global__ void cl_alive_max(const double* __restrict__ M, const uint8_t* __restrict__ alive, int64_t n,
+                             unsigned long long* out /* [0]=ordered max, [1]=nan flag */) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / n, c = i - r * n;
+        if (!alive[r] || !alive[c]) continue;
+        const double v = M[i];
+        if (v != v) atomicExch(out + 1, 1ULL);
+        else atomicMax(out + 0, cl_ord(v));
+    }
+}
+
+inline size_t cl_smem_bytes(int64_t n) {
+    return CL_WARPS * sizeof(WarpScratch) + REC * sizeof(double) + CL_WARPS * sizeof(ClBest) + 2 * sizeof(double)
+           + (size_t)((n + 31) / 32) * sizeof(uint32_t) + 16;
+}
+
+inline cudaError_t cluster_configure() {
+    return cudaFuncSetAttribute(cl_merge_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+}  // namespace spk

@@ -1,0 +1,95 @@
+// common.cuh - context, error plumbing and small helpers shared by the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/spkdiar.h"
+#include "layout.cuh"
+
+namespace spk {
+
+constexpr int D39 = SPKDIAR_DIM;
+using L39 = Layout<D39>;
+constexpr int REC = L39::REC;                 // 820 doubles per record
+static_assert(REC == SPKDIAR_RECORD, "header / kernel record size disagree");
+
+}  // namespace spk
+
+struct spkdiar_ctx {
+    int device = 0;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    char err[512] = {0};
+    int64_t launches = 0;
+    bool prof = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double prof_ms[SPKDIAR_NPROF] = {0};
+    int64_t prof_n[SPKDIAR_NPROF] = {0};
+};
+
+struct spkdiar_feat {
+    spkdiar_ctx* ctx = nullptr;
+    const float* x = nullptr;     // (n, dim) frame-major fp32 in HBM
+    bool own_x = false;
+    int64_t n = 0;
+    int32_t dim = 0;
+    double* P = nullptr;          // (n + 1) prefix records, lane-paired layout
+    double* shift = nullptr;      // 40 doubles: per-file shift subtracted before accumulation
+    double* tile = nullptr;       // per-tile sums / exclusive tile prefixes
+    int64_t ntiles = 0;
+};
+
+namespace spk {
+
+inline int set_err(spkdiar_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define SPK_CUDA(ctx, call)                                                        \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess)                                                    \
+            return spk::set_err((ctx), SPKDIAR_E_CUDA, "%s failed: %s (%s:%d)", #call, \
+                                cudaGetErrorString(e__), __FILE__, __LINE__);      \
+    } while (0)
+
+// scope timer for one kernel class (only when profiling is on)
+struct Prof {
+    spkdiar_ctx* c; int k; int64_t n0;
+    Prof(spkdiar_ctx* ctx, int klass) : c(ctx), k(klass), n0(ctx->launches) {
+        if (c->prof) cudaEventRecord(c->ev0, c->stream);
+    }
+    ~Prof() {
+        if (c->prof) {
+            cudaEventRecord(c->ev1, c->stream);
+            cudaEventSynchronize(c->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            c->prof_ms[k] += ms;
+            c->prof_n[k] += c->launches - n0;
+        }
+    }
+};
+
+template <class T>
+struct DevBuf {                      // RAII device buffer
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc((void**)&p, count * sizeof(T) + 16); }
+};
+
+__device__ __forceinline__ double d_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+}  // namespace spk

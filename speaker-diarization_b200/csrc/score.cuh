@@ -1,0 +1,281 @@
+// score.cuh - K2: batched window / pair scoring, one warp per log-determinant.
+//
+// Replaces the bodies of bic / glr / kl2 (spk-change-detection.py:72-133,
+// spk-clustering.py:81-133).  The arithmetic that combines log-determinants
+// into a distance mirrors the reference expression by expression (explicit
+// _rn intrinsics: no FMA contraction), so that the only deviation from the
+// reference is the last-bits difference between an LDL^T log-determinant and
+// np.log(scipy.linalg.det(.)).
+#pragma once
+
+#include "common.cuh"
+#include "ldl.cuh"
+
+namespace spk {
+
+constexpr int SC_WARPS = 4;                 // warps per CTA in the scoring kernels
+constexpr int SC_THREADS = SC_WARPS * 32;
+
+// ---- distance formulas (fp64, reference operation order) ----------------------------
+// BIC, spk-change-detection.py:95-99 / spk-clustering.py:95-99:
+//   d = 0.5*N*ln|S| - 0.5*N1*ln|S1| - 0.5*N2*ln|S2|;  d -= lambda*0.5*(p+0.5*p*(p+1))*ln N
+__host__ __device__ inline double bic_penalty(double lambda, double N) {
+    const double p = (double)D39;
+    const double k = (lambda * 0.5) * (p + 0.5 * p * (p + 1.0));
+    return k * log(N);
+}
+__device__ __forceinline__ double bic_combine(double N1, double N2, double ld1, double ld2,
+                                              double ld, double lambda) {
+    const double N = N1 + N2;
+    const double t0 = __dmul_rn(__dmul_rn(0.5, N), ld);
+    const double c1 = __dmul_rn(__dmul_rn(0.5, N1), ld1);
+    const double t2 = __dmul_rn(__dmul_rn(0.5, N2), ld2);
+    double d = __dsub_rn(__dsub_rn(t0, c1), t2);
+    const double p = (double)D39;
+    const double k = __dmul_rn(__dmul_rn(lambda, 0.5), __dadd_rn(p, __dmul_rn(__dmul_rn(0.5, p), p + 1.0)));
+    return __dsub_rn(d, __dmul_rn(k, log(N)));
+}
+// GLR, spk-change-detection.py:114-115:
+//   d = -(N/2) * ((N1/N)*ln|S1| + (N2/N)*ln|S2| - ln|(N1/N) S1 + (N2/N) S2|)
+__device__ __forceinline__ double glr_combine(double N1, double N2, double ld1, double ld2, double ldm) {
+    const double N = N1 + N2;
+    const double a = __dmul_rn(__ddiv_rn(N1, N), ld1);
+    const double b = __dmul_rn(__ddiv_rn(N2, N), ld2);
+    const double s = __dsub_rn(__dadd_rn(a, b), ldm);
+    return __dmul_rn(-__ddiv_rn(N, 2.0), s);
+}
+__device__ __forceinline__ void glr_weights(double N1, double N2, double& wx, double& wy) {
+    const double N = N1 + N2;
+    wx = (N1 / N) / (N1 - 1.0);           // (N1/N) * S1 with S1 = M1/(N1-1)
+    wy = (N2 / N) / (N2 - 1.0);
+}
+__device__ __forceinline__ double range_map(double v) {     // np.log(det()) range, Q12
+    if (v < -744.4400719213812) return -d_inf();
+    if (v > 709.782712893384) return d_inf();
+    return v;
+}
+
+// ---- one log-determinant term of a candidate ------------------------------------------
+// term 0: left [a,m)   term 1: right [m,b)   term 2: pooled [a,b) (BIC) or the GLR mix
+template <class SrcX, class SrcY>
+__device__ __forceinline__ double logdet_term(int term, int metric, const SrcX& X, const SrcY& Y,
+                                              WarpScratch& w, int lane) {
+    double hi[D39];
+    double lo[L39::NLO];
+    int kind = term == 0 ? FORM_X : (term == 1 ? FORM_Y : (metric == SPKDIAR_BIC ? FORM_POOL : FORM_MIX));
+    double wx = 1.0, wy = 1.0;
+    if (kind == FORM_MIX) glr_weights(X(L39::CNT), Y(L39::CNT), wx, wy);
+    const double n = form_matrix<D39>(hi, lo, kind, X, Y, wx, wy, w, lane);
+    const double lm = ldl_logdet<D39, false>(hi, lo, w, lane);
+    if (kind == FORM_MIX) return range_map(lm);
+    return finish_logdet(lm, n, D39);
+}
+
+// ---- windows of one recording: candidate k = (a, m, b) -----------------------------------
+__global__ void __launch_bounds__(SC_THREADS, 3)
+win_terms_kernel(const double* __restrict__ P, const int64_t* __restrict__ a,
+                 const int64_t* __restrict__ m, const int64_t* __restrict__ b,
+                 int64_t ncand, int metric, double* __restrict__ terms) {
+    __shared__ __align__(16) WarpScratch ws[SC_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntask = ncand * 3;
+    for (int64_t id = (int64_t)blockIdx.x * SC_WARPS + warp; id < ntask; id += (int64_t)gridDim.x * SC_WARPS) {
+        const int64_t k = id / 3;
+        const int term = (int)(id - 3 * k);
+        const WinSrc X{P + m[k] * REC, P + a[k] * REC};
+        const WinSrc Y{P + b[k] * REC, P + m[k] * REC};
+        const double v = logdet_term(term, metric, X, Y, ws[warp], lane);
+        if (lane == 0) terms[id] = v;
+    }
+}
+
+__global__ void win_combine_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ m,
+                                   const int64_t* __restrict__ b, int64_t ncand, int metric,
+                                   double lambda, const double* __restrict__ terms,
+                                   double* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ncand) return;
+    const double N1 = (double)(m[k] - a[k]), N2 = (double)(b[k] - m[k]);
+    const double* t = terms + 3 * k;
+    out[k] = metric == SPKDIAR_BIC ? bic_combine(N1, N2, t[0], t[1], t[2], lambda)
+                                   : glr_combine(N1, N2, t[0], t[1], t[2]);
+}
+
+// ---- KL2 (reference semantics: diagonal-only formula, float32 sequential means) ----------
+// spk-change-detection.py:124-133, SURVEY.md Q3 / Q4.
+struct Kl2Scratch {
+    WarpScratch w;
+    double Lsm[(D39 * (D39 - 1)) / 2 + 3];
+    double pinv[VS];
+    double dS[2][VS];      // diag(S) of side 0 / 1
+    double dP[2][VS];      // diag(S^-1)
+    float  mean[2][VS];    // float32 means
+};
+
+// float32 sequential mean over the concatenation of `nr` frame ranges, exactly
+// as np.mean(arr, 0) accumulates a float32 matrix row by row
+__device__ __forceinline__ void seq_mean_f32(const float* __restrict__ x, const int64_t* ra,
+                                             const int64_t* rb, int64_t nr, int lane, float* out) {
+    float s0 = 0.f, s1 = 0.f;
+    int64_t cnt = 0;
+    const bool second = lane + 32 < D39;
+    for (int64_t r = 0; r < nr; ++r) {
+        const int64_t a = ra[r], b = rb[r];
+        cnt += b - a;
+        int64_t t = a;
+        for (; t + 4 <= b; t += 4) {
+            float u[4], v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                u[k] = __ldg(x + (t + k) * D39 + lane);
+                v[k] = second ? __ldg(x + (t + k) * D39 + lane + 32) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { s0 = __fadd_rn(s0, u[k]); s1 = __fadd_rn(s1, v[k]); }
+        }
+        for (; t < b; ++t) {
+            s0 = __fadd_rn(s0, __ldg(x + t * D39 + lane));
+            if (second) s1 = __fadd_rn(s1, __ldg(x + t * D39 + lane + 32));
+        }
+    }
+    const float fn = (float)cnt;
+    out[lane] = __fdiv_rn(s0, fn);
+    if (second) out[lane + 32] = __fdiv_rn(s1, fn);
+}
+
+// both sides of a KL2 evaluation: diag(S), diag(S^-1) into scratch.  The loop is
+// deliberately not unrolled: one copy of the factorisation per kernel.
+template <class Src>
+__device__ __forceinline__ void kl2_sides(const Src& X, const Src& Y, Kl2Scratch& k, int lane) {
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        const Src src = side ? Y : X;
+        double hi[D39];
+        double lo[L39::NLO];
+        const double n = form_matrix<D39>(hi, lo, FORM_X, src, src, 1.0, 1.0, k.w, lane);
+        const double rn1 = 1.0 / (n - 1.0);
+        for (int j = lane; j < D39; j += 32) {
+            const double s = k.w.s0[j];
+            k.dS[side][j] = (src(L39::pos_diag(j)) - s * s / n) * rn1;
+        }
+        const double lm = ldl_logdet<D39, true>(hi, lo, k.w, lane, k.Lsm, k.pinv);
+        double ga, gb;
+        inv_diag<D39>(k.Lsm, k.pinv, lane, ga, gb);
+        const bool bad = !(lm == lm);
+        if (lane < L39::NL) {
+            k.dP[side][lane] = bad ? d_nan() : ga * (n - 1.0);
+            k.dP[side][D39 - 1 - lane] = bad ? d_nan() : gb * (n - 1.0);
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ double kl2_finish(Kl2Scratch& k, int lane, double* t1_out, double* t2_out) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int j = lane; j < D39; j += 32) {
+        const double delta = (double)__fsub_rn(k.mean[0][j], k.mean[1][j]);
+        t1 += (k.dS[0][j] - k.dS[1][j]) * (k.dP[1][j] - k.dP[0][j]);
+        t2 += __dmul_rn(__dmul_rn(k.dP[0][j] + k.dP[1][j], delta), delta);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    }
+    *t1_out = t1; *t2_out = t2;
+    return __dadd_rn(__dmul_rn(0.5, t1), __dmul_rn(0.5, t2));
+}
+
+__global__ void __launch_bounds__(SC_THREADS, 2)
+win_kl2_kernel(const double* __restrict__ P, const float* __restrict__ x,
+               const int64_t* __restrict__ a, const int64_t* __restrict__ m,
+               const int64_t* __restrict__ b, int64_t ncand, double* __restrict__ out,
+               double* __restrict__ terms) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Kl2Scratch* ks = reinterpret_cast<Kl2Scratch*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Kl2Scratch& k = ks[warp];
+    for (int64_t id = (int64_t)blockIdx.x * SC_WARPS + warp; id < ncand; id += (int64_t)gridDim.x * SC_WARPS) {
+        const int64_t aa = a[id], mm = m[id], bb = b[id];
+        kl2_sides(WinSrc{P + mm * REC, P + aa * REC}, WinSrc{P + bb * REC, P + mm * REC}, k, lane);
+        seq_mean_f32(x, &aa, &mm, 1, lane, k.mean[0]);
+        seq_mean_f32(x, &mm, &bb, 1, lane, k.mean[1]);
+        __syncwarp();
+        double t1, t2;
+        const double d = kl2_finish(k, lane, &t1, &t2);
+        if (lane == 0) {
+            out[id] = d;
+            if (terms) { terms[3 * id] = t1; terms[3 * id + 1] = t2; terms[3 * id + 2] = 0.0; }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- sets of frame ranges (clusters given by the host) -----------------------------------
+// record of a set = sum over its ranges of (P[b] - P[a]), plain cluster record
+__global__ void __launch_bounds__(256)
+set_records_kernel(const double* __restrict__ P, const int64_t* __restrict__ off,
+                   const int64_t* __restrict__ ra, const int64_t* __restrict__ rb,
+                   int64_t nsets, double* __restrict__ rec) {
+    const int64_t s = blockIdx.x;
+    if (s >= nsets) return;
+    for (int q = threadIdx.x; q < REC; q += blockDim.x) {
+        double acc = 0.0;
+        for (int64_t r = off[s]; r < off[s + 1]; ++r) acc += __ldg(P + rb[r] * REC + q) - __ldg(P + ra[r] * REC + q);
+        rec[s * REC + q] = acc;
+    }
+}
+
+// pair p scores record recX[p] against recY[p]
+__global__ void __launch_bounds__(SC_THREADS, 3)
+pair_terms_kernel(const double* recX, const double* recY, int64_t npairs, int metric,
+                  double* __restrict__ terms) {
+    __shared__ __align__(16) WarpScratch ws[SC_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntask = npairs * 3;
+    for (int64_t id = (int64_t)blockIdx.x * SC_WARPS + warp; id < ntask; id += (int64_t)gridDim.x * SC_WARPS) {
+        const int64_t k = id / 3;
+        const int term = (int)(id - 3 * k);
+        const RecSrc X{recX + k * REC};
+        const RecSrc Y{recY + k * REC};
+        const double v = logdet_term(term, metric, X, Y, ws[warp], lane);
+        if (lane == 0) terms[id] = v;
+    }
+}
+
+__global__ void pair_combine_kernel(const double* __restrict__ recX, const double* __restrict__ recY,
+                                    int64_t npairs, int metric, double lambda,
+                                    const double* __restrict__ terms, double* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= npairs) return;
+    const double N1 = recX[k * REC + L39::CNT], N2 = recY[k * REC + L39::CNT];
+    const double* t = terms + 3 * k;
+    out[k] = metric == SPKDIAR_BIC ? bic_combine(N1, N2, t[0], t[1], t[2], lambda)
+                                   : glr_combine(N1, N2, t[0], t[1], t[2]);
+}
+
+__global__ void __launch_bounds__(SC_THREADS, 2)
+pair_kl2_kernel(const double* recX, const double* recY, const float* __restrict__ x,
+                const int64_t* __restrict__ off1, const int64_t* __restrict__ a1, const int64_t* __restrict__ b1,
+                const int64_t* __restrict__ off2, const int64_t* __restrict__ a2, const int64_t* __restrict__ b2,
+                int64_t npairs, double* __restrict__ out, double* __restrict__ terms) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Kl2Scratch* ks = reinterpret_cast<Kl2Scratch*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Kl2Scratch& k = ks[warp];
+    for (int64_t id = (int64_t)blockIdx.x * SC_WARPS + warp; id < npairs; id += (int64_t)gridDim.x * SC_WARPS) {
+        kl2_sides(RecSrc{recX + id * REC}, RecSrc{recY + id * REC}, k, lane);
+        seq_mean_f32(x, a1 + off1[id], b1 + off1[id], off1[id + 1] - off1[id], lane, k.mean[0]);
+        seq_mean_f32(x, a2 + off2[id], b2 + off2[id], off2[id + 1] - off2[id], lane, k.mean[1]);
+        __syncwarp();
+        double t1, t2;
+        const double d = kl2_finish(k, lane, &t1, &t2);
+        if (lane == 0) {
+            out[id] = d;
+            if (terms) { terms[3 * id] = t1; terms[3 * id + 1] = t2; terms[3 * id + 2] = 0.0; }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace spk

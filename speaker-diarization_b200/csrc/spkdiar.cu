@@ -1,0 +1,362 @@
+// spkdiar.cu - libspkdiar.so: the C-ABI of include/spkdiar.h over the sm_100a kernels.
+//
+// One translation unit: context + frame statistics (stats.cuh), batched scoring
+// (score.cuh), the persistent growing-window driver (gw.cuh) and the
+// agglomerative clustering engine (cluster.cuh).
+//
+// Build (see __graft_entry__.build()):
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
+//        -shared -Xcompiler -fPIC -o libspkdiar.so spkdiar.cu
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "stats.cuh"
+#include "score.cuh"
+#include "gw.cuh"
+#include "cluster.cuh"
+
+using namespace spk;
+
+static thread_local char g_create_err[512] = "";
+
+static int grid_for(const spkdiar_ctx* c, int64_t tasks, int per_cta, int ctas_per_sm) {
+    int64_t want = (tasks + per_cta - 1) / per_cta;
+    int64_t cap = (int64_t)c->sms * ctas_per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+extern "C" {
+
+int spkdiar_abi_version(void) { return SPKDIAR_ABI_VERSION; }
+
+int spkdiar_create(int device, void* stream, spkdiar_ctx** out) {
+    if (!out) return SPKDIAR_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        snprintf(g_create_err, sizeof(g_create_err), "no CUDA device: %s",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return SPKDIAR_E_NODEVICE;
+    }
+    if (device < 0 || device >= ndev) {
+        snprintf(g_create_err, sizeof(g_create_err), "device %d out of range (have %d)", device, ndev);
+        return SPKDIAR_E_ARG;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        snprintf(g_create_err, sizeof(g_create_err), "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+        return SPKDIAR_E_CUDA;
+    }
+    if (prop.major != 10) {
+        snprintf(g_create_err, sizeof(g_create_err),
+                 "device %d is sm_%d%d; this library carries sm_100a code only (no fallback)",
+                 device, prop.major, prop.minor);
+        return SPKDIAR_E_NODEVICE;
+    }
+    spkdiar_ctx* c = new (std::nothrow) spkdiar_ctx();
+    if (!c) return SPKDIAR_E_NOMEM;
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) goto fail;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) goto fail;
+        c->own_stream = true;
+    }
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) goto fail;
+    if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) goto fail;
+    {
+        uint8_t row[REC], col[REC];
+        fill_lut(row, col);
+        if ((e = cudaMemcpyToSymbol(c_row, row, sizeof(row))) != cudaSuccess) goto fail;
+        if ((e = cudaMemcpyToSymbol(c_col, col, sizeof(col))) != cudaSuccess) goto fail;
+    }
+    if ((e = cudaFuncSetAttribute(win_kl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SC_WARPS * sizeof(Kl2Scratch)))) != cudaSuccess) goto fail;
+    if ((e = cudaFuncSetAttribute(pair_kl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(SC_WARPS * sizeof(Kl2Scratch)))) != cudaSuccess) goto fail;
+    if ((e = gw_configure()) != cudaSuccess) goto fail;
+    if ((e = cluster_configure()) != cudaSuccess) goto fail;
+    *out = c;
+    return SPKDIAR_OK;
+fail:
+    snprintf(g_create_err, sizeof(g_create_err), "context setup failed: %s", cudaGetErrorString(e));
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SPKDIAR_E_CUDA;
+}
+
+void spkdiar_destroy(spkdiar_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* spkdiar_last_error(const spkdiar_ctx* c) { return c ? c->err : g_create_err; }
+int64_t spkdiar_launch_count(const spkdiar_ctx* c) { return c ? c->launches : 0; }
+int spkdiar_sm_count(const spkdiar_ctx* c) { return c ? c->sms : 0; }
+
+int spkdiar_profile_enable(spkdiar_ctx* c, int enable) {
+    if (!c) return SPKDIAR_E_ARG;
+    c->prof = enable != 0;
+    for (int k = 0; k < SPKDIAR_NPROF; ++k) { c->prof_ms[k] = 0.0; c->prof_n[k] = 0; }
+    return SPKDIAR_OK;
+}
+
+int spkdiar_profile_read(const spkdiar_ctx* c, double* ms, int64_t* launches) {
+    if (!c) return SPKDIAR_E_ARG;
+    for (int k = 0; k < SPKDIAR_NPROF; ++k) {
+        if (ms) ms[k] = c->prof_ms[k];
+        if (launches) launches[k] = c->prof_n[k];
+    }
+    return SPKDIAR_OK;
+}
+
+// ---- features + K1 ------------------------------------------------------------------------
+
+static int feat_alloc(spkdiar_ctx* c, int64_t n, int32_t dim, spkdiar_feat** out) {
+    if (!c || !out) return SPKDIAR_E_ARG;
+    *out = nullptr;
+    if (n < 0) return set_err(c, SPKDIAR_E_ARG, "negative frame count %lld", (long long)n);
+    if (dim != D39)
+        return set_err(c, SPKDIAR_E_UNSUPPORTED,
+                       "feature dimension %d: the kernels are specialised for %d (fconfig.cfg) and there is no fallback",
+                       dim, D39);
+    SPK_CUDA(c, cudaSetDevice(c->device));
+    spkdiar_feat* f = new (std::nothrow) spkdiar_feat();
+    if (!f) return set_err(c, SPKDIAR_E_NOMEM, "host allocation failed");
+    f->ctx = c; f->n = n; f->dim = dim;
+    f->ntiles = (n + K1_TILE - 1) / K1_TILE;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&f->P, (size_t)(n + 1) * REC * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&f->shift, K1_XS * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&f->tile, (size_t)std::max<int64_t>(f->ntiles, 1) * REC * sizeof(double))) != cudaSuccess) {
+        if (f->P) cudaFree(f->P);
+        if (f->shift) cudaFree(f->shift);
+        delete f;
+        return set_err(c, e == cudaErrorMemoryAllocation ? SPKDIAR_E_NOMEM : SPKDIAR_E_CUDA,
+                       "device allocation for %lld frames failed: %s", (long long)n, cudaGetErrorString(e));
+    }
+    *out = f;
+    return SPKDIAR_OK;
+}
+
+int spkdiar_stats_build(spkdiar_feat* f) {
+    if (!f) return SPKDIAR_E_ARG;
+    spkdiar_ctx* c = f->ctx;
+    SPK_CUDA(c, cudaSetDevice(c->device));
+    {
+        Prof p(c, SPKDIAR_PROF_STATS);
+        if (f->n == 0) {
+            SPK_CUDA(c, cudaMemsetAsync(f->P, 0, REC * sizeof(double), c->stream));
+        } else {
+            k1_shift<<<1, 1024, 0, c->stream>>>(f->x, f->n, f->shift);
+            k1_tile_sums<<<(unsigned)f->ntiles, K1_THREADS, 0, c->stream>>>(f->x, f->n, f->shift, f->tile);
+            k1_tile_scan<<<(REC + 127) / 128, 128, 0, c->stream>>>(f->tile, f->ntiles);
+            k1_tile_write<<<(unsigned)f->ntiles, K1_THREADS, 0, c->stream>>>(f->x, f->n, f->shift, f->tile, f->P);
+            c->launches += 4;
+        }
+    }
+    SPK_CUDA(c, cudaGetLastError());
+    SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SPKDIAR_OK;
+}
+
+int spkdiar_features_upload(spkdiar_ctx* c, const float* frames, int64_t n, int32_t dim, spkdiar_feat** out) {
+    if (!c || !out || (!frames && n > 0)) return c ? set_err(c, SPKDIAR_E_ARG, "null argument") : SPKDIAR_E_ARG;
+    int rc = feat_alloc(c, n, dim, out);
+    if (rc) return rc;
+    spkdiar_feat* f = *out;
+    float* dx = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dx, (size_t)std::max<int64_t>(n, 1) * dim * sizeof(float));
+    if (e != cudaSuccess) {
+        spkdiar_features_free(f); *out = nullptr;
+        return set_err(c, SPKDIAR_E_NOMEM, "device allocation for the frames failed: %s", cudaGetErrorString(e));
+    }
+    f->x = dx; f->own_x = true;
+    {
+        Prof p(c, SPKDIAR_PROF_H2D);
+        if (n > 0) e = cudaMemcpyAsync(dx, frames, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    }
+    if (e != cudaSuccess) {
+        spkdiar_features_free(f); *out = nullptr;
+        return set_err(c, SPKDIAR_E_CUDA, "feature upload failed: %s", cudaGetErrorString(e));
+    }
+    rc = spkdiar_stats_build(f);
+    if (rc) { spkdiar_features_free(f); *out = nullptr; }
+    return rc;
+}
+
+int spkdiar_features_adopt(spkdiar_ctx* c, const float* dev_frames, int64_t n, int32_t dim, spkdiar_feat** out) {
+    if (!c || !out || (!dev_frames && n > 0)) return c ? set_err(c, SPKDIAR_E_ARG, "null argument") : SPKDIAR_E_ARG;
+    int rc = feat_alloc(c, n, dim, out);
+    if (rc) return rc;
+    (*out)->x = dev_frames;
+    rc = spkdiar_stats_build(*out);
+    if (rc) { spkdiar_features_free(*out); *out = nullptr; }
+    return rc;
+}
+
+int spkdiar_features_free(spkdiar_feat* f) {
+    if (!f) return SPKDIAR_OK;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    if (f->P) cudaFree(f->P);
+    if (f->shift) cudaFree(f->shift);
+    if (f->tile) cudaFree(f->tile);
+    if (f->own_x && f->x) cudaFree(const_cast<float*>(f->x));
+    delete f;
+    return SPKDIAR_OK;
+}
+
+int64_t spkdiar_features_frames(const spkdiar_feat* f) { return f ? f->n : -1; }
+
+int spkdiar_stats_window(spkdiar_feat* f, int64_t a, int64_t b, double* out819, double* shift39) {
+    if (!f || !out819) return SPKDIAR_E_ARG;
+    spkdiar_ctx* c = f->ctx;
+    if (a < 0 || b < a || b > f->n) return set_err(c, SPKDIAR_E_ARG, "window [%lld,%lld) outside 0..%lld",
+                                                  (long long)a, (long long)b, (long long)f->n);
+    SPK_CUDA(c, cudaSetDevice(c->device));
+    std::vector<double> ra(REC), rb(REC);
+    SPK_CUDA(c, cudaMemcpyAsync(ra.data(), f->P + a * REC, REC * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SPK_CUDA(c, cudaMemcpyAsync(rb.data(), f->P + b * REC, REC * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (shift39) SPK_CUDA(c, cudaMemcpyAsync(shift39, f->shift, D39 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < D39; ++j) out819[j] = rb[L39::VEC + j] - ra[L39::VEC + j];
+    for (int r = 0; r < D39; ++r)
+        for (int k = 0; k <= r; ++k) out819[D39 + r * (r + 1) / 2 + k] = rb[L39::pos(r, k)] - ra[L39::pos(r, k)];
+    if ((int64_t)(rb[L39::CNT] - ra[L39::CNT]) != b - a)
+        return set_err(c, SPKDIAR_E_CUDA, "prefix count mismatch: %g vs %lld", rb[L39::CNT] - ra[L39::CNT], (long long)(b - a));
+    return SPKDIAR_OK;
+}
+
+// ---- K2 ---------------------------------------------------------------------------------
+
+static int check_metric(spkdiar_ctx* c, int metric) {
+    if (metric != SPKDIAR_GLR && metric != SPKDIAR_BIC && metric != SPKDIAR_KL2)
+        return set_err(c, SPKDIAR_E_ARG, "unknown metric %d", metric);
+    return SPKDIAR_OK;
+}
+
+int spkdiar_score_windows(spkdiar_feat* f, const int64_t* a, const int64_t* m, const int64_t* b,
+                          int64_t ncand, int metric, double lambda, double* out_d, double* out_terms) {
+    if (!f) return SPKDIAR_E_ARG;
+    spkdiar_ctx* c = f->ctx;
+    if (ncand < 0 || (ncand > 0 && (!a || !m || !b || !out_d))) return set_err(c, SPKDIAR_E_ARG, "null argument");
+    if (int rc = check_metric(c, metric)) return rc;
+    if (ncand == 0) return SPKDIAR_OK;
+    for (int64_t k = 0; k < ncand; ++k)
+        if (a[k] < 0 || m[k] < a[k] || b[k] < m[k] || b[k] > f->n)
+            return set_err(c, SPKDIAR_E_ARG, "candidate %lld = (%lld,%lld,%lld) outside 0..%lld", (long long)k,
+                           (long long)a[k], (long long)m[k], (long long)b[k], (long long)f->n);
+    SPK_CUDA(c, cudaSetDevice(c->device));
+    DevBuf<int64_t> idx; DevBuf<double> terms, dout;
+    SPK_CUDA(c, idx.alloc(3 * ncand));
+    SPK_CUDA(c, terms.alloc(3 * ncand));
+    SPK_CUDA(c, dout.alloc(ncand));
+    int64_t *da = idx.p, *dm = idx.p + ncand, *db = idx.p + 2 * ncand;
+    const size_t nb = ncand * sizeof(int64_t);
+    SPK_CUDA(c, cudaMemcpyAsync(da, a, nb, cudaMemcpyHostToDevice, c->stream));
+    SPK_CUDA(c, cudaMemcpyAsync(dm, m, nb, cudaMemcpyHostToDevice, c->stream));
+    SPK_CUDA(c, cudaMemcpyAsync(db, b, nb, cudaMemcpyHostToDevice, c->stream));
+    {
+        Prof p(c, SPKDIAR_PROF_SCORE);
+        if (metric == SPKDIAR_KL2) {
+            win_kl2_kernel<<<grid_for(c, ncand, SC_WARPS, 2), SC_THREADS, SC_WARPS * sizeof(Kl2Scratch), c->stream>>>(
+                f->P, f->x, da, dm, db, ncand, dout.p, terms.p);
+            c->launches += 1;
+        } else {
+            win_terms_kernel<<<grid_for(c, 3 * ncand, SC_WARPS, 3), SC_THREADS, 0, c->stream>>>(
+                f->P, da, dm, db, ncand, metric, terms.p);
+            win_combine_kernel<<<(unsigned)((ncand + 127) / 128), 128, 0, c->stream>>>(
+                da, dm, db, ncand, metric, lambda, terms.p, dout.p);
+            c->launches += 2;
+        }
+    }
+    SPK_CUDA(c, cudaGetLastError());
+    SPK_CUDA(c, cudaMemcpyAsync(out_d, dout.p, ncand * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (out_terms)
+        SPK_CUDA(c, cudaMemcpyAsync(out_terms, terms.p, 3 * ncand * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SPKDIAR_OK;
+}
+
+int spkdiar_score_sets(spkdiar_feat* f, int64_t npairs,
+                       const int64_t* off1, const int64_t* a1, const int64_t* b1,
+                       const int64_t* off2, const int64_t* a2, const int64_t* b2,
+                       int metric, double lambda, double* out_d, double* out_terms) {
+    if (!f) return SPKDIAR_E_ARG;
+    spkdiar_ctx* c = f->ctx;
+    if (npairs < 0 || (npairs > 0 && (!off1 || !a1 || !b1 || !off2 || !a2 || !b2 || !out_d)))
+        return set_err(c, SPKDIAR_E_ARG, "null argument");
+    if (int rc = check_metric(c, metric)) return rc;
+    if (npairs == 0) return SPKDIAR_OK;
+    const int64_t nr1 = off1[npairs], nr2 = off2[npairs];
+    for (int side = 0; side < 2; ++side) {
+        const int64_t* ra = side ? a2 : a1; const int64_t* rb = side ? b2 : b1;
+        const int64_t nr = side ? nr2 : nr1;
+        for (int64_t r = 0; r < nr; ++r)
+            if (ra[r] < 0 || rb[r] < ra[r] || rb[r] > f->n)
+                return set_err(c, SPKDIAR_E_ARG, "range %lld of set list %d = [%lld,%lld) outside 0..%lld",
+                               (long long)r, side + 1, (long long)ra[r], (long long)rb[r], (long long)f->n);
+    }
+    SPK_CUDA(c, cudaSetDevice(c->device));
+    DevBuf<int64_t> idx; DevBuf<double> rec, terms, dout;
+    const int64_t nidx = 2 * (npairs + 1) + 2 * nr1 + 2 * nr2;
+    SPK_CUDA(c, idx.alloc(nidx));
+    SPK_CUDA(c, rec.alloc(2 * npairs * REC));
+    SPK_CUDA(c, terms.alloc(3 * npairs));
+    SPK_CUDA(c, dout.alloc(npairs));
+    int64_t* d_off1 = idx.p; int64_t* d_off2 = d_off1 + npairs + 1;
+    int64_t* d_a1 = d_off2 + npairs + 1; int64_t* d_b1 = d_a1 + nr1;
+    int64_t* d_a2 = d_b1 + nr1; int64_t* d_b2 = d_a2 + nr2;
+    SPK_CUDA(c, cudaMemcpyAsync(d_off1, off1, (npairs + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    SPK_CUDA(c, cudaMemcpyAsync(d_off2, off2, (npairs + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if (nr1) {
+        SPK_CUDA(c, cudaMemcpyAsync(d_a1, a1, nr1 * 8, cudaMemcpyHostToDevice, c->stream));
+        SPK_CUDA(c, cudaMemcpyAsync(d_b1, b1, nr1 * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (nr2) {
+        SPK_CUDA(c, cudaMemcpyAsync(d_a2, a2, nr2 * 8, cudaMemcpyHostToDevice, c->stream));
+        SPK_CUDA(c, cudaMemcpyAsync(d_b2, b2, nr2 * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    double* recX = rec.p; double* recY = rec.p + npairs * REC;
+    {
+        Prof p(c, SPKDIAR_PROF_SCORE);
+        set_records_kernel<<<(unsigned)npairs, 256, 0, c->stream>>>(f->P, d_off1, d_a1, d_b1, npairs, recX);
+        set_records_kernel<<<(unsigned)npairs, 256, 0, c->stream>>>(f->P, d_off2, d_a2, d_b2, npairs, recY);
+        if (metric == SPKDIAR_KL2) {
+            pair_kl2_kernel<<<grid_for(c, npairs, SC_WARPS, 2), SC_THREADS, SC_WARPS * sizeof(Kl2Scratch), c->stream>>>(
+                recX, recY, f->x, d_off1, d_a1, d_b1, d_off2, d_a2, d_b2, npairs, dout.p, terms.p);
+            c->launches += 3;
+        } else {
+            pair_terms_kernel<<<grid_for(c, 3 * npairs, SC_WARPS, 3), SC_THREADS, 0, c->stream>>>(
+                recX, recY, npairs, metric, terms.p);
+            pair_combine_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, c->stream>>>(
+                recX, recY, npairs, metric, lambda, terms.p, dout.p);
+            c->launches += 4;
+        }
+    }
+    SPK_CUDA(c, cudaGetLastError());
+    SPK_CUDA(c, cudaMemcpyAsync(out_d, dout.p, npairs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (out_terms)
+        SPK_CUDA(c, cudaMemcpyAsync(out_terms, terms.p, 3 * npairs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SPK_CUDA(c, cudaStreamSynchronize(c->stream));
+    return SPKDIAR_OK;
+}
+
+}  // extern "C"
+
+#include "abi_gw.inc"
+#include "abi_cluster.inc"
