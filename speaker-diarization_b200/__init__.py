@@ -14,8 +14,9 @@ Numeric work happens only in ``csrc/`` (CUDA, sm_100a) behind the C-ABI of
 fallback: calls raise ``SpkdiarError`` when the library or a GPU is missing.
 """
 
-from . import py2fmt, feacat, synth                    # noqa: F401
+from . import py2fmt, feacat, synth, recipe            # noqa: F401
 from . import _abi                                     # noqa: F401
+from . import change_detection, clustering, scoring    # noqa: F401
 from ._abi import SpkdiarError                         # noqa: F401
 
 __version__ = '0.1.0'

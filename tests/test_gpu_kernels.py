@@ -1,0 +1,201 @@
+"""GPU parity tests of the kernels, through the C-ABI (ctypes), against the CPU
+oracle on the same seeded inputs.
+
+Tolerances (fp64): a distance is a difference of terms 0.5*N*ln|S| that are
+10^3..10^5 in size, so "1e-9 relative" is stated against the LARGEST TERM
+(hard parts): |d_gpu - d_ref| <= 1e-9 * max(|d_ref|, terms).
+Measured agreement is 1e-13..1e-10.  The reference's KL2 inverts covariances of
+as few as 40 frames in 39 dimensions (condition numbers 1e4..1e7), where LAPACK's
+SVD pseudo-inverse and an LDL^T inverse legitimately differ by cond * eps; for
+windows shorter than 2*d frames the KL2 bound is 1e-6, else 1e-9."""
+
+import numpy as np
+import pytest
+
+import spkdiar                              # noqa: F401
+from spkdiar import _abi, synth
+from oracle import distances as OD
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    c = _abi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope='module')
+def rec():
+    return synth.make_recording(5, 30000, 4)
+
+
+@pytest.fixture(scope='module')
+def feat(ctx, rec):
+    f = ctx.upload(rec.frames)
+    yield f
+    f.close()
+
+
+def test_prefix_statistics_match_numpy(feat, rec):
+    """K1: window statistics from prefix differences == direct fp64 sums."""
+    x = rec.frames
+    for a, b in [(0, 30000), (0, 1), (29999, 30000), (100, 160), (127, 129), (128, 256), (12345, 17000), (7, 7)]:
+        s, q, shift = feat.stats_window(a, b)
+        xc = x[a:b].astype(np.float64) - shift
+        s_ref = xc.sum(0)
+        q_ref = (xc.T @ xc)[np.tril_indices(39)]
+        # error budget: a few ulp of the PREFIX magnitude (30000 frames, |x|^2 ~ 3)
+        assert np.max(np.abs(s - s_ref)) <= 1e-8, (a, b)
+        assert np.max(np.abs(q - q_ref)) <= 1e-8, (a, b)
+        if b > a:
+            cov = (q_ref - 0)  # silence linters
+            assert np.all(np.isfinite(q))
+
+
+def test_prefix_is_deterministic(ctx, rec):
+    """Two builds of the statistics are bit-identical (no timing-dependent
+    association in the scan)."""
+    f1, f2 = ctx.upload(rec.frames), ctx.upload(rec.frames)
+    try:
+        for a, b in [(0, 30000), (513, 20111)]:
+            s1, q1, _ = f1.stats_window(a, b)
+            s2, q2, _ = f2.stats_window(a, b)
+            assert np.array_equal(s1, s2) and np.array_equal(q1, q2)
+    finally:
+        f1.close()
+        f2.close()
+
+
+def _cands(n, total, seed, lo=40, hi=2500):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, total - 2 * hi, n)
+    m = a + rng.integers(lo, hi, n)
+    b = m + rng.integers(lo, hi, n)
+    return a, m, b
+
+
+@pytest.mark.parametrize('lam', [1.0, 1.3])
+def test_bic_windows(feat, rec, lam):
+    x = rec.frames
+    a, m, b = _cands(200, 30000, 1)
+    d, t = feat.score_windows(a, m, b, _abi.BIC, lam, terms=True)
+    for k in range(len(a)):
+        ref = OD.bic_cd(x[a[k]:m[k]], x[m[k]:b[k]], x[a[k]:b[k]], lam)
+        scale = max(abs(ref), 0.5 * (b[k] - a[k]) * abs(t[k, 2]), 0.5 * (m[k] - a[k]) * abs(t[k, 0]))
+        assert abs(d[k] - ref) <= TOL * scale, (k, d[k], ref)
+        # the terms are the reference's log-determinants
+        ld = np.log(np.linalg.det(np.cov(x[a[k]:b[k]], rowvar=0)))
+        assert abs(t[k, 2] - ld) <= 1e-10 * abs(ld)
+
+
+def test_glr_windows(feat, rec):
+    x = rec.frames
+    a, m, b = _cands(200, 30000, 2)
+    d, t = feat.score_windows(a, m, b, _abi.GLR, terms=True)
+    for k in range(len(a)):
+        ref = OD.glr(x[a[k]:m[k]], x[m[k]:b[k]])
+        scale = max(abs(ref), 0.5 * (b[k] - a[k]) * np.max(np.abs(t[k])))
+        assert abs(d[k] - ref) <= TOL * scale, (k, d[k], ref)
+
+
+def test_kl2_windows(feat, rec):
+    x = rec.frames
+    a, m, b = _cands(150, 30000, 3)
+    d, t = feat.score_windows(a, m, b, _abi.KL2, terms=True)
+    for k in range(len(a)):
+        ref = OD.kl2(x[a[k]:m[k]], x[m[k]:b[k]])
+        short = min(m[k] - a[k], b[k] - m[k]) < 2 * 39
+        scale = max(abs(ref), abs(t[k, 0]), abs(t[k, 1]))
+        assert abs(d[k] - ref) <= (1e-6 if short else TOL) * scale, (k, d[k], ref, m[k] - a[k], b[k] - m[k])
+
+
+def test_far_offset_windows_keep_precision(ctx):
+    """Catastrophic-cancellation guard: short windows at the END of a long
+    recording with a large mean offset (prefix sums are ~1e7 there)."""
+    rec = synth.make_recording(8, 200000, 3)
+    x = rec.frames + np.float32(25.0)             # un-normalised features: mean 25 sigma
+    f = ctx.upload(x)
+    try:
+        a = np.array([199000, 199500, 150000, 100]); m = a + 150; b = m + 120
+        d = f.score_windows(a, m, b, _abi.BIC, 1.0)
+        for k in range(len(a)):
+            ref = OD.bic_cd(x[a[k]:m[k]], x[m[k]:b[k]], x[a[k]:b[k]], 1.0)
+            assert abs(d[k] - ref) <= 1e-7 * max(abs(ref), 1e3), (k, d[k], ref)
+    finally:
+        f.close()
+
+
+def test_score_sets_matches_concatenated_frames(feat, rec):
+    """Clusters given as lists of ranges == the reference's concatenate + cov."""
+    x = rec.frames
+    s1 = [[(0, 300), (900, 1250)], [(5000, 5600)], [(100, 180), (400, 470), (20000, 20100)]]
+    s2 = [[(2000, 2400)], [(7000, 7300), (7400, 7800)], [(25000, 25900)]]
+    for name, met in (('BIC', _abi.BIC), ('GLR', _abi.GLR), ('KL2', _abi.KL2)):
+        d = feat.score_sets(s1, s2, met, 1.3)
+        for k in range(3):
+            a1 = np.concatenate([x[a:b] for a, b in s1[k]])
+            a2 = np.concatenate([x[a:b] for a, b in s2[k]])
+            ref = {'BIC': lambda: OD.bic_cl(a1, a2, 1.3), 'GLR': lambda: OD.glr(a1, a2),
+                   'KL2': lambda: OD.kl2(a1, a2)}[name]()
+            assert abs(d[k] - ref) <= 1e-9 * max(abs(ref), 1e3), (name, k, d[k], ref)
+
+
+def test_degenerate_windows_do_not_crash(ctx):
+    """Edge cases the reference maps to nan / inf: constant
+    frames (singular covariance), windows shorter than the dimension."""
+    x = np.ones((2000, 39), dtype=np.float32)
+    x[1000:] = np.random.default_rng(0).standard_normal((1000, 39)).astype(np.float32)
+    f = ctx.upload(x)
+    try:
+        d = f.score_windows([0, 1000, 1000], [200, 1020, 1300], [400, 1040, 1600], _abi.BIC, 1.0)
+        assert not np.isfinite(d[0])            # |S| = 0 everywhere
+        assert not np.isfinite(d[1]) or abs(d[1]) > 0   # 20-frame windows in 39 dims: singular
+        assert np.isfinite(d[2])
+        g = f.score_windows([0], [200], [400], _abi.GLR)
+        k = f.score_windows([0], [200], [400], _abi.KL2)
+        assert not np.isfinite(g[0]) and not np.isfinite(k[0])
+    finally:
+        f.close()
+
+
+def test_argument_errors(ctx, feat):
+    with pytest.raises(_abi.SpkdiarError) as e:
+        ctx.upload(np.zeros((10, 13), dtype=np.float32))
+    assert e.value.code == -5 and '39' in str(e.value)
+    with pytest.raises(_abi.SpkdiarError):
+        feat.score_windows([0], [10], [10 ** 9], _abi.BIC)
+    with pytest.raises(_abi.SpkdiarError):
+        feat.score_windows([5], [3], [10], _abi.BIC)
+    with pytest.raises(_abi.SpkdiarError):
+        feat.score_windows([0], [50], [100], 7)
+    assert len(feat.score_windows([], [], [], _abi.BIC)) == 0
+    with pytest.raises(_abi.SpkdiarError):
+        feat.gw_run([0], [10 ** 9], 100.0, 100.0, 300.0, 10.0, 0.0, 1.0, _abi.BIC)
+
+
+def test_empty_recording(ctx):
+    f = ctx.upload(np.zeros((0, 39), dtype=np.float32))
+    try:
+        assert f.n == 0
+        win, first = f.gw_run([0], [0], 100.0, 100.0, 300.0, 10.0, 0.0, 1.0, _abi.BIC)
+        assert len(win) == 0 and list(first) == [0, 0]
+    finally:
+        f.close()
+
+
+def test_adopt_device_memory_equals_upload(ctx, rec):
+    """features_adopt over a torch CUDA tensor == features_upload of the same data."""
+    import torch
+    t = torch.from_numpy(rec.frames).cuda()
+    torch.cuda.synchronize()
+    fa = ctx.adopt(t.data_ptr(), t.shape[0])
+    fu = ctx.upload(rec.frames)
+    try:
+        a, m, b = _cands(20, 30000, 9)
+        assert np.array_equal(fa.score_windows(a, m, b, _abi.BIC), fu.score_windows(a, m, b, _abi.BIC))
+    finally:
+        fa.close()
+        fu.close()

@@ -1,0 +1,209 @@
+"""GPU end-to-end parity: the drop-in command lines must write byte-identical
+recipes and the same log (numbers to 1e-9) as the reference did on the same
+synthetic inputs (committed golden fixtures made from the reference itself),
+and agree with the CPU oracle on further seeded cases."""
+
+import io
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import spkdiar                              # noqa: F401
+from conftest import load_golden, logs_match, run_oracle, run_product
+from spkdiar import _abi, synth
+from spkdiar import change_detection as pcd, clustering as pcl
+from spkdiar.recipe import Line
+from oracle import change_detection as ocd, clustering as ocl
+
+pytestmark = pytest.mark.gpu
+
+# KL2 inverts near-singular 40-frame covariances: its printed numbers carry cond*eps
+LOG_TOL = {'gw_kl2': 1e-6, 'sw_kl2_tt': 1e-6, 'cl2_hi_kl2': 1e-6}
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    c = _abi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize('name', sorted(cases.CASES))
+def test_cli_reproduces_reference_golden(name, tmp_path, ctx):
+    kind, variant, _, flags = cases.CASES[name]
+    gold = load_golden(name)
+    rpath, feadir, sha, _ = cases.materialise(name, str(tmp_path))
+    assert sha == gold['frames_sha256']
+    out = str(tmp_path / 'out.recipe')
+    argv = [rpath, feadir, '-o', out] + flags
+    if 'raises' in gold:
+        with pytest.raises(ValueError) as e:
+            run_product(kind, variant, argv + ['--sw-bic', 'strict'], ctx)
+        assert 'ValueError: %s' % e.value == gold['raises']
+        return
+    stdout, _ = run_product(kind, variant, argv, ctx)
+    assert open(out).read() == gold['recipe']
+    bad = logs_match(stdout.replace(str(tmp_path), '<TMP>'), gold['stdout'], LOG_TOL.get(name, 1e-9))
+    assert bad is None, bad
+
+
+def _case(tmp_path, seed, n, k, kind='one', rate=100, **kw):
+    rec = synth.make_recording(seed, n, k, rate=rate, **kw)
+    lines = synth.one_line_recipe('/syn/t.wav', rec) if kind == 'one' else synth.turn_recipe('/syn/t.wav', rec)
+    return synth.write_case(str(tmp_path), 't', rec, lines) + (rec,)
+
+
+@pytest.mark.parametrize('flags', [
+    ['-f', '100', '-m', 'sw', '-d', 'BIC'],                                   # Q1 intent + Q2 reference memo
+    ['-f', '100', '-m', 'sw', '-d', 'BIC', '--bic-cache', 'correct', '-t', '-100'],
+    ['-f', '100', '-m', 'sw', '-d', 'GLR', '-t', '2500', '-w', '2.0', '-st', '0.25', '-tt'],
+    ['-f', '125', '-m', 'gw', '-d', 'BIC', '-w', '1.0', '-st', '3.0', '-dws', '0.1', '-l', '1.0', '-tt'],
+    ['-f', '100', '-m', 'gw', '-d', 'BIC', '-w', '3.0', '-st', '3.0', '-l', '1.0'],   # spk-diarization.py:143-145
+    ['-f', '100', '-m', 'gw', '-d', 'BIC'],                                   # script defaults: -w 5 -st 0.5 -dws 0.05
+    ['-f', '101', '-m', 'gw', '-d', 'BIC', '-w', '1.0', '-st', '3.0', '-dws', '0.1', '-l', '1.0'],  # non-dyadic istep
+])
+def test_change_detection_matches_oracle(flags, tmp_path, ctx):
+    rate = int(flags[1])
+    rpath, feadir, rec = _case(tmp_path, 31, 90 * rate, 4, rate=rate)
+    og, pg = str(tmp_path / 'o.recipe'), str(tmp_path / 'p.recipe')
+    so, _ = run_oracle('cd', 0, [rpath, feadir, '-o', og] + flags)
+    sp, det = run_product('cd', 0, [rpath, feadir, '-o', pg] + flags, ctx)
+    assert open(pg).read() == open(og).read()
+    bad = logs_match(sp.replace(pg, 'X'), so.replace(og, 'X'))
+    assert bad is None, bad
+    assert det.windows_visited > 0
+
+
+def test_gw_persistent_kernel_equals_host_driven_loop(tmp_path, ctx):
+    """The device-resident search and the host-driven loop (one scoring call
+    per window) visit the same windows and write the same recipe."""
+    rec = synth.make_recording(77, 15000, 4)
+    feat = ctx.upload(rec.frames)
+    try:
+        res = []
+        for on_device in (True, False):
+            det = pcd.Detector(100, 'gw', 'BIC', 1.0, 3.0, 0.1, 0.0, 1.0, ctx=ctx, gw_on_device=on_device)
+            out = io.StringIO()
+            det.detect_changes([Line('/x.wav', 'a_1', 0.0, 150.0)], out, loader=lambda l: feat)
+            res.append((out.getvalue(), det.windows_visited, det.stats.total_dist, det.stats.total_det_dist))
+        assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
+        assert abs(res[0][2] - res[1][2]) <= 1e-9 * abs(res[1][2])
+    finally:
+        feat.close()
+
+
+def test_gw_records_independent_of_group_shape_and_repeatable(ctx):
+    """Chains are independent: the records do not depend on how many chains run
+    concurrently (group size 148 CTAs ... 1 CTA), and two runs are bit-identical."""
+    rec = synth.make_recording(78, 40000, 5)
+    feat = ctx.upload(rec.frames)
+    try:
+        sa = [0, 9000, 9100, 21000, 33000, 39900]
+        sb = [9000, 9100, 21000, 33000, 39900, 40000]          # includes chains too short for a window
+        base = None
+        for mg in (1, 2, 0, 0):
+            win, first = feat.gw_run(sa, sb, 100.0, 100.0, 300.0, 10.0, 0.0, 1.0, _abi.BIC, max_groups=mg)
+            key = (win.tobytes(), first.tobytes())
+            if base is None:
+                base = key
+            assert key == base
+        assert first[2] - first[1] == 0 and first[6] - first[5] == 0
+    finally:
+        feat.close()
+
+
+def test_gw_many_chains_vs_oracle(ctx):
+    """More chains than SMs (one CTA per group, chains pulled from the queue)."""
+    rec = synth.make_recording(79, 180 * 700, 3, turn_lo=2, turn_hi=5)
+    feat = ctx.upload(rec.frames)
+    try:
+        sa = [700 * k for k in range(180)]
+        sb = [700 * (k + 1) for k in range(180)]
+        win, first = feat.gw_run(sa, sb, 100.0, 100.0, 300.0, 10.0, 0.0, 1.0, _abi.BIC)
+        cd = ocd.ChangeDetection(100, 'gw', 'BIC', 1.0, 3.0, 0.1, 0.0, 1.0)
+        for k in (0, 57, 148, 179):
+            tr = []
+            cd.trace = tr
+            cd.dist_gw(rec.frames[sa[k]:sb[k]], ('/x.wav', 'a_1', 0.0, 7.0), io.StringIO())
+            got = win[first[k]:first[k + 1]]
+            assert len(got) == len(tr)
+            for r, w in zip(tr, got):
+                assert r['start'] == w['start'] and r['end'] == w['end'] and bool(r['positive']) == bool(w['positive'])
+                if r['positive']:
+                    assert r['maxi_fine'] == w['maxi_fine']
+    finally:
+        feat.close()
+
+
+@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('dist,thr', [('BIC', 0.0), ('GLR', 700.0)])
+def test_device_merge_loop_equals_host_driven_loop(variant, dist, thr, ctx):
+    """The persistent merge kernel and the host-driven loop (numpy matrix, device
+    distances) produce the same merge sequence - including variant 2's stale
+    entries."""
+    rec = synth.make_recording(301, 9000, 5, turn_lo=1, turn_hi=4)
+    feat = ctx.upload(rec.frames)
+    recipe = [Line('/x.wav', 'a_%d' % (k + 1), a / 100.0, b / 100.0) for k, (a, b, _) in enumerate(rec.turns)]
+    try:
+        res = []
+        for engine in ('device', 'host'):
+            cl = pcl.Clusterer(100, variant, 'hi', dist, thr, 0, 2.0, ctx=ctx, engine=engine)
+            out = io.StringIO()
+            cl.process_recipe(recipe, out, loader=lambda l: feat)
+            res.append((out.getvalue(), [(a, b) for a, b, _ in cl.merges], [d for _, _, d in cl.merges],
+                        cl.max_dist, cl.min_dist))
+        assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
+        assert np.allclose(res[0][2], res[1][2], rtol=1e-12, atol=0)
+        assert np.isclose(float(res[0][3]), float(res[1][3]), rtol=1e-12) or res[0][3] == res[1][3]
+        assert np.isclose(float(res[0][4]), float(res[1][4]), rtol=1e-12)
+    finally:
+        feat.close()
+
+
+def test_clustering_max_spk_forces_merges(tmp_path, ctx):
+    rpath, feadir, rec = _case(tmp_path, 41, 7000, 4, kind='turns', turn_lo=2, turn_hi=5)
+    for variant in (1, 2):
+        og, pg = str(tmp_path / 'o.recipe'), str(tmp_path / 'p.recipe')
+        flags = ['-f', '100', '-m', 'hi', '-t', '-1e9', '-ms', '2']
+        so, _ = run_oracle('cl', variant, [rpath, feadir, '-o', og] + flags)
+        sp, _ = run_product('cl', variant, [rpath, feadir, '-o', pg] + flags, ctx)
+        assert open(pg).read() == open(og).read()
+        assert logs_match(sp.replace(pg, 'X'), so.replace(og, 'X')) is None
+        assert 'Final speakers: 2' in sp
+
+
+def test_single_segment_and_tiny_recipes(tmp_path, ctx):
+    rec = synth.make_recording(5, 900, 1)
+    rpath, feadir = synth.write_case(str(tmp_path), 't', rec, synth.one_line_recipe('/syn/t.wav', rec))
+    for kind, variant, flags in (('cl', 1, ['-f', '100']), ('cl', 2, ['-f', '100']),
+                                 ('cd', 0, ['-f', '100', '-m', 'gw', '-d', 'BIC', '-w', '5.0']),   # 2*winsize > n
+                                 ('cd', 0, ['-f', '100', '-m', 'sw', '-d', 'GLR'])):
+        og, pg = str(tmp_path / 'o.recipe'), str(tmp_path / 'p.recipe')
+        so, _ = run_oracle(kind, variant, [rpath, feadir, '-o', og] + flags)
+        sp, _ = run_product(kind, variant, [rpath, feadir, '-o', pg] + flags, ctx)
+        assert open(pg).read() == open(og).read()
+        assert logs_match(sp.replace(pg, 'X'), so.replace(og, 'X')) is None
+
+
+def test_scoring_tools_agree_on_gpu_and_oracle_outputs(tmp_path, ctx):
+    """north_star: spk-change-performance.py and clus-performance.py report
+    identical scores for the GPU's and the oracle's outputs."""
+    from spkdiar import scoring
+    rec = synth.make_recording(91, 20000, 4)
+    rpath, feadir = synth.write_case(str(tmp_path), 't', rec, synth.one_line_recipe('/syn/t.wav', rec))
+    truth = str(tmp_path / 'truth.recipe')
+    open(truth, 'w').writelines(synth.truth_recipe('/syn/t.wav', rec))
+    outs = {}
+    for who, run in (('o', run_oracle), ('p', run_product)):
+        seg, clu = str(tmp_path / (who + '_seg.recipe')), str(tmp_path / (who + '_clu.recipe'))
+        extra = [ctx] if who == 'p' else []
+        run('cd', 0, [rpath, feadir, '-o', seg, '-f', '100'] + cases.D2_GW, *extra)
+        run('cl', 1, [seg, feadir, '-o', clu, '-f', '100', '-m', 'hi', '-l', '1.3'], *extra)
+        a, b = io.StringIO(), io.StringIO()
+        scoring.change_performance_main([truth, seg], stdout=a)
+        scoring.clus_performance_main([truth, clu], stdout=b)
+        outs[who] = (open(seg).read(), open(clu).read(), a.getvalue(), b.getvalue())
+    assert outs['o'] == outs['p']
+    assert 'DER:' in outs['p'][3]
