@@ -1,0 +1,388 @@
+#!/usr/bin/env python3
+"""bench.py - the headline benchmark: audio-hours/sec diarized.
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "config 2"): ONE
+synthetic 1-hour recording (360,000 feacat-format MFCC frames, d = 39, 100 fps,
+K = 8 speakers, turns 3..19 s, seed 1002).  One STEP is the whole hot path over
+that recording:
+
+  1. frame statistics (fp64 prefix sums)                         K1
+  2. growing-window change detection with BIC  (spk-diarization2's flags:
+     -m gw -d BIC -w 1.0 -st 3.0 -dws 0.1 -l 1.0)                K3
+  3. the same search with GLR (-t GLR_T) and with KL2 (-t KL2_T)  K3
+  4. agglomerative BIC clustering of the BIC turns
+     (spk-clustering.py -m hi -l 1.3)                            K6 / K7
+
+and counts as ONE audio-hour diarized (the GLR and KL2 passes are extra work
+the config names, not extra audio).  `value` runs it with the frames already in
+HBM through the low-level C-ABI; `e2e` runs it through the public drop-in API
+(`Detector` / `Clusterer`, recipe text in, recipe text out) with the frames in
+pinned HOST memory, the host->device copy and the host-side replay inside the
+timed region.
+
+N > 1 (torchrun): recordings are independent, so every rank diarizes its own
+1-hour recording (seed 1002 + rank) with no data-path collective - weak scaling.
+
+`--impl reference` times the reference's own CPU implementation (the oracle: the
+reference scripts are Python 2 and cannot run here; the oracle is their
+Python-3 restatement, pinned against them - see oracle/__init__.py) on a bounded
+sample of the same workload.
+"""
+
+import argparse
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RATE = 100
+FRAMES = 360000
+GW_FLAGS = dict(winsize=1.0, winstep=3.0, deltaws=0.1)
+# thresholds tuned once on seed 1002 with the script's own end-of-run metrics so that the
+# number of detected changes is about the number of true turns, then frozen
+GLR_T = 1150.0
+KL2_T = 700.0
+CPU_SAMPLE_SECONDS = 150            # audio seconds of the CPU-baseline sample
+
+# algorithmic work per unit (restated in DESIGN.md)
+FLOP_LOGDET = 22893.0               # form 39x39 from prefix differences + factorise
+FLOP_KL2 = 85332.0
+BYTES_STATS_PER_FRAME = 2 * 156 + 6560
+
+
+def make_recording(rank):
+    import spkdiar                                   # noqa: F401
+    from spkdiar import synth
+    return synth.make_recording(1002 + rank, FRAMES, 8, rate=RATE)
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 9 for k in range(4)
+                          if r[5 + k].lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def segments_from_windows(win, nframes):
+    """Turn boundaries (frames) from the growing-window records of one chain."""
+    cuts = [0.0]
+    for r in win:
+        if r['positive']:
+            cuts.append(float(r['start']) + float(r['maxi_fine']))
+    cuts.append(float(nframes))
+    a = [int(c) for c in cuts[:-1]]
+    b = [int(c) for c in cuts[1:]]
+    return a, b
+
+
+def device_step(ctx, dev_ptr, nframes):
+    """One step with the frames resident in HBM (low-level C-ABI)."""
+    from spkdiar import _abi
+    W, ST, DW = GW_FLAGS['winsize'] * RATE, GW_FLAGS['winstep'] * RATE, float(int(RATE * GW_FLAGS['deltaws']))
+    feat = ctx.adopt(dev_ptr, nframes)
+    out = {}
+    try:
+        for name, met, thr in (('BIC', _abi.BIC, 0.0), ('GLR', _abi.GLR, GLR_T), ('KL2', _abi.KL2, KL2_T)):
+            win, _ = feat.gw_run([0], [nframes], float(RATE), W, ST, DW, thr, 1.0, met)
+            out[name] = win
+        sa, sb = segments_from_windows(out['BIC'], nframes)
+        with feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
+            merges, _ = cl.run(0.0, 0, 1)
+        out['merges'] = merges
+        out['nseg'] = len(sa)
+    finally:
+        feat.close()
+    return out
+
+
+def e2e_step(ctx, host_frames, recipe_lines):
+    """One step through the public drop-in API with HOST buffers: recipe text in,
+    recipe text out; H2D copy, device work, D2H of the records and the host-side
+    replay are all inside."""
+    from spkdiar import change_detection as pcd, clustering as pcl, recipe
+    parsed = recipe.parse(recipe_lines)
+    feat = ctx.upload_ptr(host_frames.data_ptr(), host_frames.shape[0])
+    texts = {}
+    try:
+        for name, thr in (('BIC', 0.0), ('GLR', GLR_T), ('KL2', KL2_T)):
+            det = pcd.Detector(RATE, 'gw', name, GW_FLAGS['winsize'], GW_FLAGS['winstep'], GW_FLAGS['deltaws'],
+                               thr, 1.0, ctx=ctx)
+            buf = io.StringIO()
+            det.detect_changes(parsed, buf, loader=lambda l: feat)
+            texts[name] = buf.getvalue()
+        cl = pcl.Clusterer(RATE, 1, 'hi', 'BIC', 0.0, 0, 1.3, ctx=ctx)
+        buf = io.StringIO()
+        cl.process_recipe(recipe.parse(texts['BIC'].splitlines(True)), buf, loader=lambda l: feat)
+        texts['clusters'] = buf.getvalue()
+    finally:
+        feat.close()
+    return texts
+
+
+def cpu_oracle_sample(seconds, rank=0, parallel=False):
+    """The reference's CPU path (oracle) on the first `seconds` of the recording:
+    the same four passes.  -> (audio_seconds, cpu_wall_seconds, cores)."""
+    import warnings
+    warnings.simplefilter('ignore')
+    rec = make_recording(rank)
+    n = int(seconds * RATE)
+    x = rec.frames[:n]
+    jobs = [('BIC', 0.0, True), ('GLR', GLR_T, False), ('KL2', KL2_T, False)]
+    t0 = time.perf_counter()
+    if parallel:
+        import multiprocessing as mp
+        with mp.get_context('fork').Pool(len(jobs)) as pool:
+            pool.starmap(_cpu_job, [(x, j) for j in jobs])
+        cores = len(jobs)
+    else:
+        for j in jobs:
+            _cpu_job(x, j)
+        cores = 1
+    return n / float(RATE), time.perf_counter() - t0, cores
+
+
+def _cpu_job(x, job):
+    from oracle import change_detection as ocd, clustering as ocl
+    name, thr, then_cluster = job
+    n = x.shape[0]
+    cd = ocd.ChangeDetection(RATE, 'gw', name, GW_FLAGS['winsize'], GW_FLAGS['winstep'], GW_FLAGS['deltaws'],
+                             thr, 1.0)
+    out = io.StringIO()
+    line = ('/syn/c2.wav', 'a_1', 0.0, n / float(RATE))
+    cd.dist_gw(x, line, out)
+    if then_cluster:
+        recipe = ocd.parse_recipe(out.getvalue().splitlines(True), lambda *a: None)
+        cl = ocl.Clustering(RATE, 1, 'hi', 'BIC', 0.0, 0, 1.3)
+        cl.process_recipe(recipe, io.StringIO(), loader=lambda rl: (39, x))
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vals = []
+    for k in range(args.warmup + args.steps):
+        audio_s, wall, cores = cpu_oracle_sample(args.cpu_seconds, 0, parallel=True)
+        if k >= args.warmup:
+            vals.append((audio_s / 3600.0) / wall)
+    v = sum(vals) / len(vals)
+    sample = ('first %d s of the 1-hour recording: oracle gw BIC -> CL1 clustering, gw GLR, gw KL2 as 3 '
+              'parallel processes (the reference is single-process Python; BLAS threads default)' % args.cpu_seconds)
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'audio_hours_per_sec_diarized', 'value': v, 'unit': 'audio-hours/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * (args.cpu_seconds / 3600.0) / v, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(),
+        'cpu_baseline': {'value': v, 'unit': 'audio-hours/s', 'cores': 3, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'audio-hours/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def workload_config():
+    return {'workload': 'config2: 1-hour synthetic recording, 360000x39 fp32 frames @100fps, growing-window '
+                        'BIC+GLR+KL2 change detection + CL1 BIC clustering of the BIC turns',
+            'frames': FRAMES, 'dim': 39, 'frame_rate': RATE, 'glr_threshold': GLR_T, 'kl2_threshold': KL2_T,
+            'l2': 'inputs larger than L2: 2.36 GB of prefix records rewritten and re-read every step (L2 = 126 MB)',
+            'parallelism': 'one recording per GPU, no collective'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-seconds', type=int, default=CPU_SAMPLE_SECONDS)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import spkdiar                                   # noqa: F401
+    from spkdiar import _abi, synth
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+
+    rec = make_recording(rank)
+    host = torch.from_numpy(rec.frames).pin_memory()
+    dev = host.cuda()
+    recipe_lines = synth.one_line_recipe('/syn/c2_%d.wav' % rank, rec)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = _abi.Context(local, stream=stream)
+    W = max(args.warmup, 3)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; device time by CUDA events on
+        the stream the library launches on; max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = None
+        for _ in range(steps):
+            res = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item()), res
+
+    # ---- device-resident arm ----
+    for _ in range(W):
+        device_step(ctx, dev.data_ptr(), FRAMES)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.profile(True)
+    l0 = ctx.launches
+    ms_total, res = timed(lambda: device_step(ctx, dev.data_ptr(), FRAMES), args.steps)
+    launches = ctx.launches - l0
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * args.steps * (FRAMES / RATE / 3600.0) / (ms_total / 1e3)
+
+    # ---- end-to-end arm (host buffers, public API) ----
+    for _ in range(2):
+        e2e_step(ctx, host, recipe_lines)
+    ms_e2e, texts = timed(lambda: e2e_step(ctx, host, recipe_lines), args.steps)
+    e2e_value = world * args.steps * (FRAMES / RATE / 3600.0) / (ms_e2e / 1e3)
+    h2d = FRAMES * 39 * 4
+    d2h = sum(len(res[k]) for k in ('BIC', 'GLR', 'KL2')) * 72 + len(res['merges']) * 16
+
+    lt = torch.tensor([launches], device='cuda', dtype=torch.int64)
+    if dist is not None:
+        dist.all_reduce(lt)
+
+    # ---- roofline of the kernel classes (per-class CUDA-event time inside the library) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except (OSError, ValueError):
+        pass
+    hbm_peak, hbm_src = (peaks['hbm_gbs'], 'measured') if 'hbm_gbs' in peaks else (6650.0, 'fallback')
+    steps = float(args.steps)
+
+    def cands(win):
+        coarse = int(np.sum(np.abs(win['ncand'])))
+        fine = int(np.sum(win['positive'])) * int(2 * RATE / 10)
+        return coarse + fine
+    flops_gw = (cands(res['BIC']) * 2 * FLOP_LOGDET + cands(res['GLR']) * 3 * FLOP_LOGDET
+                + cands(res['KL2']) * FLOP_KL2)
+    nseg = res['nseg']
+    flops_merge = (len(res['merges']) * nseg / 2.0) * (FLOP_LOGDET + 820)
+    flops_score = (nseg * (nseg - 1) / 2.0 + nseg) * (FLOP_LOGDET + 820)
+    kern = {
+        'stats': {'bound': 'hbm', 'unit': 'GB/s', 'peak': hbm_peak, 'peak_source': hbm_src,
+                  'work': 3 * FRAMES * BYTES_STATS_PER_FRAME / 3.0},      # one build per step
+        'gw': {'bound': 'fp64', 'unit': 'TFLOP/s', 'peak': 37.2, 'peak_source': 'nominal 148 SM x 64 DFMA/clk x 1.965 GHz',
+               'work': flops_gw},
+        'score': {'bound': 'fp64', 'unit': 'TFLOP/s', 'peak': 37.2, 'peak_source': 'nominal', 'work': flops_score},
+        'merge': {'bound': 'fp64', 'unit': 'TFLOP/s', 'peak': 37.2, 'peak_source': 'nominal', 'work': flops_merge},
+    }
+    rl_all = {}
+    for k, spec in kern.items():
+        ms_k, n_k = prof[k]
+        if ms_k <= 0:
+            continue
+        per_step_s = ms_k / steps / 1e3
+        scale = 1e9 if spec['unit'] == 'GB/s' else 1e12
+        ach = spec['work'] / per_step_s / scale
+        rl_all[k] = {'bound': spec['bound'], 'achieved': ach, 'peak': spec['peak'], 'unit': spec['unit'],
+                     'frac': ach / spec['peak'], 'peak_source': spec['peak_source'],
+                     'ms_per_step': ms_k / steps, 'launches_per_step': n_k / steps, 'traffic': None}
+    dominant = max(rl_all, key=lambda k: rl_all[k]['ms_per_step'])
+    roofline = dict(rl_all[dominant], kernel=dominant)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        audio_s, wall, cores = cpu_oracle_sample(args.cpu_seconds)
+        cpu = {'value': (audio_s / 3600.0) / wall, 'unit': 'audio-hours/s', 'cores': cores, 'kind': 'port',
+               'sample': 'first %d s of the same recording, same four passes, oracle (py3 restatement of the '
+                         'reference scripts), one process' % args.cpu_seconds,
+               'seconds': wall}
+
+    if rank == 0:
+        line = {
+            'metric': 'audio_hours_per_sec_diarized', 'value': value, 'unit': 'audio-hours/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': W, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': workload_config(),
+            'frames_per_sec': value * 3600.0 * RATE,
+            'e2e': {'value': e2e_value, 'unit': 'audio-hours/s', 'h2d_bytes_per_step': h2d,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / args.steps},
+            'gpu_launches': int(lt.item()),
+            'clocks': clocks,
+            'roofline': roofline,
+            'roofline_all': rl_all,
+            'cpu_baseline': cpu,
+            'result': {'bic_changes': int(np.sum(res['BIC']['positive'])), 'glr_changes': int(np.sum(res['GLR']['positive'])),
+                       'kl2_changes': int(np.sum(res['KL2']['positive'])), 'true_turns': len(rec.turns),
+                       'windows': {k: int(len(res[k])) for k in ('BIC', 'GLR', 'KL2')},
+                       'segments_clustered': nseg, 'merges': int(len(res['merges'])),
+                       'final_speakers': nseg - int(len(res['merges']))},
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

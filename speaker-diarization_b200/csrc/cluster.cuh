@@ -79,12 +79,11 @@ __device__ __forceinline__ void cl_track(double d, unsigned long long* stat) {  
 }
 
 __global__ void __launch_bounds__(256)
-cl_init_records(const double* __restrict__ P, const int64_t* __restrict__ seg, int64_t n,
+cl_init_records(const Stats st, const int64_t* __restrict__ seg, int64_t n,
                 double* __restrict__ rec) {
     const int64_t s = blockIdx.x;
-    const double* pa = P + seg[s] * REC;
-    const double* pb = P + seg[n + s] * REC;
-    for (int q = threadIdx.x; q < REC; q += blockDim.x) rec[s * REC + q] = __ldg(pb + q) - __ldg(pa + q);
+    const WinSrc w(st, seg[s], seg[n + s], REC);
+    for (int q = threadIdx.x; q < REC; q += blockDim.x) rec[s * REC + q] = w(q);
 }
 
 __global__ void __launch_bounds__(SC_THREADS, 3)

@@ -38,7 +38,8 @@ struct spkdiar_feat {
     bool own_x = false;
     int64_t n = 0;
     int32_t dim = 0;
-    double* P = nullptr;          // (n + 1) prefix records, lane-paired layout
+    double* P = nullptr;          // (n + 1) block-local prefix records, lane-paired layout
+    double2* C = nullptr;         // (ntiles + 1) double-double block prefix records
     double* shift = nullptr;      // 40 doubles: per-file shift subtracted before accumulation
     double* tile = nullptr;       // per-tile sums / exclusive tile prefixes
     int64_t ntiles = 0;

@@ -39,7 +39,7 @@ constexpr int GW_JMAX = 128;            // fine-tune candidates (2*istep + 1 <= 
 #define GW_NEG_INIT (-9223372036854775808.0)   /* -sys.maxint - 1 as a double, CD:203 */
 
 struct GwDev {                 // kernel parameters
-    const double* P;           // prefix records
+    Stats st;                  // two-level frame statistics
     const float* x;            // frames (KL2 means)
     const double* T;           // candidate offset table, kmax entries
     int64_t kmax;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                 double v;
                 if (KL2) {
                     Kl2Scratch& ks = reinterpret_cast<Kl2Scratch*>(scratch_base)[warp];
-                    kl2_sides(WinSrc{g.P + mm * REC, g.P + s0 * REC}, WinSrc{g.P + ee * REC, g.P + mm * REC}, ks, lane);
+                    kl2_sides(WinSrc(g.st, s0, mm, REC), WinSrc(g.st, mm, ee, REC), ks, lane);
                     seq_mean_f32(g.x, &s0, &mm, 1, lane, ks.mean[0]);
                     seq_mean_f32(g.x, &mm, &ee, 1, lane, ks.mean[1]);
                     __syncwarp();
@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     __syncwarp();
                 } else {
                     WarpScratch& wsr = reinterpret_cast<WarpScratch*>(scratch_base)[warp];
-                    const WinSrc X{g.P + mm * REC, g.P + s0 * REC};
-                    const WinSrc Y{g.P + ee * REC, g.P + mm * REC};
+                    const WinSrc X(g.st, s0, mm, REC);
+                    const WinSrc Y(g.st, mm, ee, REC);
                     v = logdet_term(term, g.metric, X, Y, wsr, lane);
                 }
                 if (lane == 0) *dst = v;

@@ -31,13 +31,32 @@ struct WarpScratch {
 // ---- operand sources ----------------------------------------------------------
 // A source yields element q of a statistics record.
 
-// frames [a, b) of a recording: difference of two prefix records.  The prefix
-// array is immutable while any scoring kernel runs -> read-only path.
+// frames [a, b) of a recording from the two-level statistics of stats.cuh:
+// block-local prefix records plus the double-double block prefix.  Both arrays
+// are immutable while any scoring kernel runs -> read-only path.
+struct Stats {
+    const double* P;       // (n + 1) block-local prefix records
+    const double2* C;      // (nblocks + 1) double-double block prefix records
+};
+constexpr int STAT_BLOCK = 128;    // == K1_TILE
 struct WinSrc {
-    const double* __restrict__ hi_;   // record at b
-    const double* __restrict__ lo_;   // record at a
+    const double* __restrict__ pb;    // record at b
+    const double* __restrict__ pa;    // record at a
+    const double2* __restrict__ cb;   // block prefix of b's block
+    const double2* __restrict__ ca;   // block prefix of a's block
+    double n;                         // b - a
+    bool cross;                       // a and b lie in different blocks
+    __device__ __forceinline__ WinSrc(const Stats& st, long long a, long long b, int rec)
+        : pb(st.P + b * rec), pa(st.P + a * rec),
+          cb(st.C + (b / STAT_BLOCK) * rec), ca(st.C + (a / STAT_BLOCK) * rec),
+          n((double)(b - a)), cross((b / STAT_BLOCK) != (a / STAT_BLOCK)) {}
     __device__ __forceinline__ double operator()(int q) const {
-        return __ldg(hi_ + q) - __ldg(lo_ + q);
+        double v = __ldg(pb + q) - __ldg(pa + q);
+        if (cross) {
+            const double2 hb = __ldg(cb + q), ha = __ldg(ca + q);
+            v += (hb.x - ha.x) + (hb.y - ha.y);
+        }
+        return v;
     }
 };
 // a cluster record that a persistent kernel may have rewritten: bypass L1.

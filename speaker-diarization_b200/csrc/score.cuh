@@ -13,6 +13,7 @@
 
 namespace spk {
 
+static_assert(STAT_BLOCK == 128, "WinSrc block size must equal K1_TILE");
 constexpr int SC_WARPS = 4;                 // warps per CTA in the scoring kernels
 constexpr int SC_THREADS = SC_WARPS * 32;
 
@@ -73,7 +74,7 @@ __device__ __forceinline__ double logdet_term(int term, int metric, const SrcX& 
 
 // ---- windows of one recording: candidate k = (a, m, b) -----------------------------------
 __global__ void __launch_bounds__(SC_THREADS, 3)
-win_terms_kernel(const double* __restrict__ P, const int64_t* __restrict__ a,
+win_terms_kernel(const Stats st, const int64_t* __restrict__ a,
                  const int64_t* __restrict__ m, const int64_t* __restrict__ b,
                  int64_t ncand, int metric, double* __restrict__ terms) {
     __shared__ __align__(16) WarpScratch ws[SC_WARPS];
@@ -82,8 +83,8 @@ win_terms_kernel(const double* __restrict__ P, const int64_t* __restrict__ a,
     for (int64_t id = (int64_t)blockIdx.x * SC_WARPS + warp; id < ntask; id += (int64_t)gridDim.x * SC_WARPS) {
         const int64_t k = id / 3;
         const int term = (int)(id - 3 * k);
-        const WinSrc X{P + m[k] * REC, P + a[k] * REC};
-        const WinSrc Y{P + b[k] * REC, P + m[k] * REC};
+        const WinSrc X(st, a[k], m[k], REC);
+        const WinSrc Y(st, m[k], b[k], REC);
         const double v = logdet_term(term, metric, X, Y, ws[warp], lane);
         if (lane == 0) terms[id] = v;
     }
@@ -187,7 +188,7 @@ __device__ __forceinline__ double kl2_finish(Kl2Scratch& k, int lane, double* t1
 }
 
 __global__ void __launch_bounds__(SC_THREADS, 2)
-win_kl2_kernel(const double* __restrict__ P, const float* __restrict__ x,
+win_kl2_kernel(const Stats st, const float* __restrict__ x,
                const int64_t* __restrict__ a, const int64_t* __restrict__ m,
                const int64_t* __restrict__ b, int64_t ncand, double* __restrict__ out,
                double* __restrict__ terms) {
@@ -197,7 +198,7 @@ win_kl2_kernel(const double* __restrict__ P, const float* __restrict__ x,
     Kl2Scratch& k = ks[warp];
     for (int64_t id = (int64_t)blockIdx.x * SC_WARPS + warp; id < ncand; id += (int64_t)gridDim.x * SC_WARPS) {
         const int64_t aa = a[id], mm = m[id], bb = b[id];
-        kl2_sides(WinSrc{P + mm * REC, P + aa * REC}, WinSrc{P + bb * REC, P + mm * REC}, k, lane);
+        kl2_sides(WinSrc(st, aa, mm, REC), WinSrc(st, mm, bb, REC), k, lane);
         seq_mean_f32(x, &aa, &mm, 1, lane, k.mean[0]);
         seq_mean_f32(x, &mm, &bb, 1, lane, k.mean[1]);
         __syncwarp();
@@ -214,14 +215,14 @@ win_kl2_kernel(const double* __restrict__ P, const float* __restrict__ x,
 // ---- sets of frame ranges (clusters given by the host) -----------------------------------
 // record of a set = sum over its ranges of (P[b] - P[a]), plain cluster record
 __global__ void __launch_bounds__(256)
-set_records_kernel(const double* __restrict__ P, const int64_t* __restrict__ off,
+set_records_kernel(const Stats st, const int64_t* __restrict__ off,
                    const int64_t* __restrict__ ra, const int64_t* __restrict__ rb,
                    int64_t nsets, double* __restrict__ rec) {
     const int64_t s = blockIdx.x;
     if (s >= nsets) return;
     for (int q = threadIdx.x; q < REC; q += blockDim.x) {
         double acc = 0.0;
-        for (int64_t r = off[s]; r < off[s + 1]; ++r) acc += __ldg(P + rb[r] * REC + q) - __ldg(P + ra[r] * REC + q);
+        for (int64_t r = off[s]; r < off[s + 1]; ++r) acc += WinSrc(st, ra[r], rb[r], REC)(q);
         rec[s * REC + q] = acc;
     }
 }

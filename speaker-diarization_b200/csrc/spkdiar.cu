@@ -140,9 +140,11 @@ static int feat_alloc(spkdiar_ctx* c, int64_t n, int32_t dim, spkdiar_feat** out
     f->ntiles = (n + K1_TILE - 1) / K1_TILE;
     cudaError_t e;
     if ((e = cudaMalloc((void**)&f->P, (size_t)(n + 1) * REC * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&f->C, (size_t)(f->ntiles + 1) * REC * sizeof(double2))) != cudaSuccess ||
         (e = cudaMalloc((void**)&f->shift, K1_XS * sizeof(double))) != cudaSuccess ||
         (e = cudaMalloc((void**)&f->tile, (size_t)std::max<int64_t>(f->ntiles, 1) * REC * sizeof(double))) != cudaSuccess) {
         if (f->P) cudaFree(f->P);
+        if (f->C) cudaFree(f->C);
         if (f->shift) cudaFree(f->shift);
         delete f;
         return set_err(c, e == cudaErrorMemoryAllocation ? SPKDIAR_E_NOMEM : SPKDIAR_E_CUDA,
@@ -160,12 +162,12 @@ int spkdiar_stats_build(spkdiar_feat* f) {
         Prof p(c, SPKDIAR_PROF_STATS);
         if (f->n == 0) {
             SPK_CUDA(c, cudaMemsetAsync(f->P, 0, REC * sizeof(double), c->stream));
+            SPK_CUDA(c, cudaMemsetAsync(f->C, 0, REC * sizeof(double2), c->stream));
         } else {
             k1_shift<<<1, 1024, 0, c->stream>>>(f->x, f->n, f->shift);
-            k1_tile_sums<<<(unsigned)f->ntiles, K1_THREADS, 0, c->stream>>>(f->x, f->n, f->shift, f->tile);
-            k1_tile_scan<<<(REC + 127) / 128, 128, 0, c->stream>>>(f->tile, f->ntiles);
             k1_tile_write<<<(unsigned)f->ntiles, K1_THREADS, 0, c->stream>>>(f->x, f->n, f->shift, f->tile, f->P);
-            c->launches += 4;
+            k1_tile_scan<<<(REC + 127) / 128, 128, 0, c->stream>>>(f->tile, f->ntiles, f->C);
+            c->launches += 3;
         }
     }
     SPK_CUDA(c, cudaGetLastError());
@@ -213,6 +215,7 @@ int spkdiar_features_free(spkdiar_feat* f) {
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
     if (f->P) cudaFree(f->P);
+    if (f->C) cudaFree(f->C);
     if (f->shift) cudaFree(f->shift);
     if (f->tile) cudaFree(f->tile);
     if (f->own_x && f->x) cudaFree(const_cast<float*>(f->x));
@@ -228,16 +231,22 @@ int spkdiar_stats_window(spkdiar_feat* f, int64_t a, int64_t b, double* out819, 
     if (a < 0 || b < a || b > f->n) return set_err(c, SPKDIAR_E_ARG, "window [%lld,%lld) outside 0..%lld",
                                                   (long long)a, (long long)b, (long long)f->n);
     SPK_CUDA(c, cudaSetDevice(c->device));
-    std::vector<double> ra(REC), rb(REC);
+    std::vector<double> ra(REC), rb(REC), ca(2 * REC), cb(2 * REC);
     SPK_CUDA(c, cudaMemcpyAsync(ra.data(), f->P + a * REC, REC * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SPK_CUDA(c, cudaMemcpyAsync(rb.data(), f->P + b * REC, REC * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SPK_CUDA(c, cudaMemcpyAsync(ca.data(), f->C + (a / K1_TILE) * REC, REC * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    SPK_CUDA(c, cudaMemcpyAsync(cb.data(), f->C + (b / K1_TILE) * REC, REC * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
     if (shift39) SPK_CUDA(c, cudaMemcpyAsync(shift39, f->shift, D39 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SPK_CUDA(c, cudaStreamSynchronize(c->stream));
-    for (int j = 0; j < D39; ++j) out819[j] = rb[L39::VEC + j] - ra[L39::VEC + j];
+    // same expression as WinSrc::operator() on the device
+    auto win = [&](int q) {
+        return (rb[q] - ra[q]) + ((cb[2 * q] - ca[2 * q]) + (cb[2 * q + 1] - ca[2 * q + 1]));
+    };
+    for (int j = 0; j < D39; ++j) out819[j] = win(L39::VEC + j);
     for (int r = 0; r < D39; ++r)
-        for (int k = 0; k <= r; ++k) out819[D39 + r * (r + 1) / 2 + k] = rb[L39::pos(r, k)] - ra[L39::pos(r, k)];
-    if ((int64_t)(rb[L39::CNT] - ra[L39::CNT]) != b - a)
-        return set_err(c, SPKDIAR_E_CUDA, "prefix count mismatch: %g vs %lld", rb[L39::CNT] - ra[L39::CNT], (long long)(b - a));
+        for (int k = 0; k <= r; ++k) out819[D39 + r * (r + 1) / 2 + k] = win(L39::pos(r, k));
+    if ((int64_t)win(L39::CNT) != b - a)
+        return set_err(c, SPKDIAR_E_CUDA, "prefix count mismatch: %g vs %lld", win(L39::CNT), (long long)(b - a));
     return SPKDIAR_OK;
 }
 
@@ -274,11 +283,11 @@ int spkdiar_score_windows(spkdiar_feat* f, const int64_t* a, const int64_t* m, c
         Prof p(c, SPKDIAR_PROF_SCORE);
         if (metric == SPKDIAR_KL2) {
             win_kl2_kernel<<<grid_for(c, ncand, SC_WARPS, 2), SC_THREADS, SC_WARPS * sizeof(Kl2Scratch), c->stream>>>(
-                f->P, f->x, da, dm, db, ncand, dout.p, terms.p);
+                Stats{f->P, f->C}, f->x, da, dm, db, ncand, dout.p, terms.p);
             c->launches += 1;
         } else {
             win_terms_kernel<<<grid_for(c, 3 * ncand, SC_WARPS, 3), SC_THREADS, 0, c->stream>>>(
-                f->P, da, dm, db, ncand, metric, terms.p);
+                Stats{f->P, f->C}, da, dm, db, ncand, metric, terms.p);
             win_combine_kernel<<<(unsigned)((ncand + 127) / 128), 128, 0, c->stream>>>(
                 da, dm, db, ncand, metric, lambda, terms.p, dout.p);
             c->launches += 2;
@@ -334,8 +343,8 @@ int spkdiar_score_sets(spkdiar_feat* f, int64_t npairs,
     double* recX = rec.p; double* recY = rec.p + npairs * REC;
     {
         Prof p(c, SPKDIAR_PROF_SCORE);
-        set_records_kernel<<<(unsigned)npairs, 256, 0, c->stream>>>(f->P, d_off1, d_a1, d_b1, npairs, recX);
-        set_records_kernel<<<(unsigned)npairs, 256, 0, c->stream>>>(f->P, d_off2, d_a2, d_b2, npairs, recY);
+        set_records_kernel<<<(unsigned)npairs, 256, 0, c->stream>>>(Stats{f->P, f->C}, d_off1, d_a1, d_b1, npairs, recX);
+        set_records_kernel<<<(unsigned)npairs, 256, 0, c->stream>>>(Stats{f->P, f->C}, d_off2, d_a2, d_b2, npairs, recY);
         if (metric == SPKDIAR_KL2) {
             pair_kl2_kernel<<<grid_for(c, npairs, SC_WARPS, 2), SC_THREADS, SC_WARPS * sizeof(Kl2Scratch), c->stream>>>(
                 recX, recY, f->x, d_off1, d_a1, d_b1, d_off2, d_a2, d_b2, npairs, dout.p, terms.p);

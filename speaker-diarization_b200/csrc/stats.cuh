@@ -2,21 +2,38 @@
 //
 // Replaces every np.cov / np.mean over a slice (spk-change-detection.py:87-94,
 // 107-108, 126-127): after this pass the sufficient statistics of ANY window
-// [a, b) are P[b] - P[a], an O(d^2) difference, instead of an O(n d^2) pass
-// over the raw frames.
+// [a, b) are an O(d^2) difference of records instead of an O(n d^2) pass over
+// the raw frames.
 //
-// HBM layout: P is (n + 1) records of REC = 820 doubles (layout.cuh), record t
-// = statistics of frames [0, t).  Frames are centred on a per-file shift vector
-// first (covariances are shift invariant; centring keeps the prefix magnitudes,
-// hence the cancellation in P[b] - P[a], small).
+// Accuracy is the design constraint.  The reference computes each window's
+// covariance directly, so its entries are good to ~eps; a plain running prefix
+// would give P[b] - P[a] an error of eps * (prefix magnitude), i.e. (t / n) eps
+// relative - 7,000 eps for a half-second window at the end of an hour - and
+// speakers with ill-conditioned covariances (cond 1e9 occurs in the synthetic
+// data) amplify that into the 1e-5 range of ln|S|.  Hence two levels:
 //
-// Three launches, all bit-reproducible run to run (a look-back scan would add
-// tile aggregates in a timing-dependent association, and change points must be
-// bit-identical between runs):
-//   A  tile_sums   one CTA per TILE frames: the 820 sums of its tile
-//   B  tile_scan   exclusive scan of the tile sums, one thread per component
-//   C  tile_write  one CTA per tile: running sums from its base, written per frame
-// Algorithmic traffic per frame: 2 x 156 B read + 6,560 B written (HBM-bound).
+//   P[t]  (n + 1 records of REC doubles, lane-paired layout, layout.cuh):
+//         statistics of frames [block_start(t), t) - the prefix RESTARTS at
+//         every block of K1_TILE = 128 frames, so its magnitude is bounded by one
+//         block;
+//   C[j]  (nblocks + 1 records of REC double2): statistics of frames
+//         [0, j * 128) as a DOUBLE-DOUBLE (hi, lo) pair, accumulated with
+//         error-free additions.
+//
+//   sum over [a, b) = (P[b] - P[a]) + ((C[jb].hi - C[ja].hi) + (C[jb].lo - C[ja].lo))
+//
+// with ja, jb the blocks of a and b; the second bracket vanishes (and is not
+// loaded) when both fall into one block.  Every window sum is then good to a
+// few eps of ITS OWN magnitude wherever it lies in the recording.
+//
+// Frames are centred on a per-file shift vector first (covariances are shift
+// invariant; centring keeps even the in-block cancellation small).
+//
+// Two launches, bit-reproducible run to run:
+//   tile_write  one CTA per block: running sums written per frame + block total
+//   tile_scan   double-double exclusive scan of the block totals, one thread per component
+// Algorithmic traffic per frame: 156 B read + 6,560 B written (HBM-bound); the
+// block level adds 13,120 B per 128 frames (+1.6 %).
 #pragma once
 
 #include "common.cuh"
@@ -95,43 +112,49 @@ __device__ __forceinline__ void k1_load_tile(const float* __restrict__ x, int64_
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(K1_THREADS) k1_tile_sums(const float* __restrict__ x, int64_t n,
-                                                           const double* __restrict__ shift,
-                                                           double* __restrict__ tile) {
-    __shared__ __align__(16) double xs[K1_TILE][K1_XS];
-    const int64_t f0 = (int64_t)blockIdx.x * K1_TILE;
-    k1_load_tile(x, n, f0, shift, xs);
-    const int q = threadIdx.x;
-    if (q >= REC) return;
-    const int r = c_row[q], c = c_col[q];
-    double a0 = 0.0, a1 = 0.0;
-#pragma unroll 8
-    for (int t = 0; t < K1_TILE; t += 2) {
-        a0 = fma(xs[t][r], xs[t][c], a0);
-        a1 = fma(xs[t + 1][r], xs[t + 1][c], a1);
-    }
-    tile[(int64_t)blockIdx.x * REC + q] = a0 + a1;
-}
-
-// exclusive scan over tiles, one thread per component, fixed left-to-right order
-__global__ void __launch_bounds__(128) k1_tile_scan(double* __restrict__ tile, int64_t ntiles) {
+// exclusive double-double scan over the block totals, one thread per component,
+// fixed left-to-right order.  C[j] = sum of totals of blocks < j.
+__global__ void __launch_bounds__(128) k1_tile_scan(const double* __restrict__ tile, int64_t ntiles,
+                                                    double2* __restrict__ C) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= REC) return;
-    double run = 0.0;
+    double hi = 0.0, lo = 0.0;
     int64_t t = 0;
     for (; t + 8 <= ntiles; t += 8) {
         double v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) v[u] = tile[(t + u) * REC + q];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { tile[(t + u) * REC + q] = run; run += v[u]; }
+        for (int u = 0; u < 8; ++u) {
+            C[(t + u) * REC + q] = make_double2(hi, lo);
+            const double s = __dadd_rn(hi, v[u]);                 // TwoSum(hi, v)
+            const double bb = __dsub_rn(s, hi);
+            const double err = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(v[u], bb));
+            lo = __dadd_rn(lo, err);
+            const double h2 = __dadd_rn(s, lo);                    // renormalise (FastTwoSum)
+            lo = __dsub_rn(lo, __dsub_rn(h2, s));
+            hi = h2;
+        }
     }
-    for (; t < ntiles; ++t) { const double v = tile[t * REC + q]; tile[t * REC + q] = run; run += v; }
+    for (; t < ntiles; ++t) {
+        const double v = tile[t * REC + q];
+        C[t * REC + q] = make_double2(hi, lo);
+        const double s = __dadd_rn(hi, v);
+        const double bb = __dsub_rn(s, hi);
+        const double err = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(v, bb));
+        lo = __dadd_rn(lo, err);
+        const double h2 = __dadd_rn(s, lo);
+        lo = __dsub_rn(lo, __dsub_rn(h2, s));
+        hi = h2;
+    }
+    C[ntiles * REC + q] = make_double2(hi, lo);
 }
 
+// one CTA per block of K1_TILE frames: P[f0] = 0, P[f0 + t + 1] = running sums
+// (t + 1 < K1_TILE), block total -> tile[]
 __global__ void __launch_bounds__(K1_THREADS) k1_tile_write(const float* __restrict__ x, int64_t n,
                                                             const double* __restrict__ shift,
-                                                            const double* __restrict__ tile,
+                                                            double* __restrict__ tile,
                                                             double* __restrict__ P) {
     __shared__ __align__(16) double xs[K1_TILE][K1_XS];
     const int64_t f0 = (int64_t)blockIdx.x * K1_TILE;
@@ -141,14 +164,19 @@ __global__ void __launch_bounds__(K1_THREADS) k1_tile_write(const float* __restr
     const int64_t left = n - f0;
     const int valid = left < K1_TILE ? (int)left : K1_TILE;
     const int r = c_row[q], c = c_col[q];
-    double acc = tile[(int64_t)blockIdx.x * REC + q];
-    double* out = P + (f0 + 1) * REC + q;
-    if (blockIdx.x == 0) P[q] = 0.0;
+    double acc = 0.0;
+    double* out = P + f0 * REC + q;
+    __stcs(out, 0.0);                              // the prefix restarts at the block boundary
 #pragma unroll 4
     for (int t = 0; t < valid; ++t) {
         acc = fma(xs[t][r], xs[t][c], acc);
-        __stcs(out + (int64_t)t * REC, acc);      // streaming store: written once, read later by other kernels
+        // streaming store: written once, read later by other kernels.  The record at the
+        // next block boundary belongs to the next block (it is that block's zero).
+        if (t + 1 < K1_TILE) __stcs(out + (int64_t)(t + 1) * REC, acc);
     }
+    tile[(int64_t)blockIdx.x * REC + q] = acc;
+    // a recording that ends exactly on a block boundary still needs its last (zero) record
+    if (valid == K1_TILE && f0 + K1_TILE == n) __stcs(out + (int64_t)K1_TILE * REC, 0.0);
 }
 
 }  // namespace spk

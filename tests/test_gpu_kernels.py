@@ -128,6 +128,34 @@ def test_far_offset_windows_keep_precision(ctx):
         f.close()
 
 
+def test_ill_conditioned_speaker(ctx):
+    """A synthetic speaker with cond(S) = 4e9 (seed 101, frames 900..1500): the
+    reference's own log-determinant is only good to cond * eps there (1e-7
+    against an 80-bit LDL^T), and ours must be no worse than a few times that -
+    this is what the two-level statistics of stats.cuh buy (a plain fp64
+    running prefix is off by 1e-5 here)."""
+    rec = synth.make_recording(seed=101, n_frames=6000, n_speakers=3)
+    x = rec.frames
+    f = ctx.upload(x)
+    try:
+        a, m, b = 900, 950, 1100
+        _, t = f.score_windows([a], [m], [b], _abi.BIC, 1.0, terms=True)
+        xs = x[a:m].astype(np.longdouble)
+        xs = xs - xs.mean(0)
+        A = xs.T @ xs / np.longdouble(m - a - 1)
+        truth = np.longdouble(0)
+        for c in range(39):
+            truth += np.log(A[c, c])
+            l = A[c + 1:, c] / A[c, c]
+            A[c + 1:, c + 1:] -= np.outer(l, A[c + 1:, c])
+        lapack = np.log(np.linalg.det(np.cov(x[a:m], rowvar=0)))
+        cond = np.linalg.cond(np.cov(x[a:m], rowvar=0))
+        assert cond > 1e9
+        assert abs(t[0, 0] - float(truth)) <= max(10 * abs(lapack - float(truth)), 64 * 2.2e-16 * cond)
+    finally:
+        f.close()
+
+
 def test_score_sets_matches_concatenated_frames(feat, rec):
     """Clusters given as lists of ranges == the reference's concatenate + cov."""
     x = rec.frames

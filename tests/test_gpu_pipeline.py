@@ -19,8 +19,14 @@ from oracle import change_detection as ocd, clustering as ocl
 
 pytestmark = pytest.mark.gpu
 
-# KL2 inverts near-singular 40-frame covariances: its printed numbers carry cond*eps
-LOG_TOL = {'gw_kl2': 1e-6, 'sw_kl2_tt': 1e-6, 'cl2_hi_kl2': 1e-6}
+# Printed numbers agree to 1e-9 except where the reference's own arithmetic is
+# conditioning-limited:
+#  * KL2 inverts near-singular 40-frame covariances: its numbers carry cond * eps;
+#  * seed 101 ('gw_bic_f100') has a speaker whose covariance has condition number 4e9:
+#    LAPACK's own ln|S| of its 50-frame windows differs from an 80-bit evaluation by 1e-7
+#    (tests/test_gpu_kernels.py::test_ill_conditioned_speaker), so two correct fp64
+#    algorithms agree to ~1e-8 there.  The recipes are still byte-identical.
+LOG_TOL = {'gw_kl2': 1e-6, 'sw_kl2_tt': 1e-6, 'cl2_hi_kl2': 1e-6, 'gw_bic_f100': 2e-8}
 
 
 @pytest.fixture(scope='module')
@@ -166,7 +172,7 @@ def test_clustering_max_spk_forces_merges(tmp_path, ctx):
     rpath, feadir, rec = _case(tmp_path, 41, 7000, 4, kind='turns', turn_lo=2, turn_hi=5)
     for variant in (1, 2):
         og, pg = str(tmp_path / 'o.recipe'), str(tmp_path / 'p.recipe')
-        flags = ['-f', '100', '-m', 'hi', '-t', '-1e9', '-ms', '2']
+        flags = ['-f', '100', '-m', 'hi', '-t=-1e9', '-ms', '2']
         so, _ = run_oracle('cl', variant, [rpath, feadir, '-o', og] + flags)
         sp, _ = run_product('cl', variant, [rpath, feadir, '-o', pg] + flags, ctx)
         assert open(pg).read() == open(og).read()
@@ -204,6 +210,7 @@ def test_scoring_tools_agree_on_gpu_and_oracle_outputs(tmp_path, ctx):
         a, b = io.StringIO(), io.StringIO()
         scoring.change_performance_main([truth, seg], stdout=a)
         scoring.clus_performance_main([truth, clu], stdout=b)
-        outs[who] = (open(seg).read(), open(clu).read(), a.getvalue(), b.getvalue())
+        outs[who] = (open(seg).read(), open(clu).read(), a.getvalue().replace(seg, 'SEG'),
+                     b.getvalue().replace(clu, 'CLU'))
     assert outs['o'] == outs['p']
     assert 'DER:' in outs['p'][3]
