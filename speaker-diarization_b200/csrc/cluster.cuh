@@ -88,7 +88,8 @@ cl_init_records(const Stats st, const int64_t* __restrict__ seg, int64_t n,
 
 __global__ void __launch_bounds__(SC_THREADS, 3)
 cl_self_logdet(const double* rec, int64_t n, double* __restrict__ ld) {
-    __shared__ __align__(16) WarpScratch ws[SC_WARPS];
+    extern __shared__ __align__(16) unsigned char sc_smem[];
+    WarpScratch* ws = reinterpret_cast<WarpScratch*>(sc_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t i = (int64_t)blockIdx.x * SC_WARPS + warp; i < n; i += (int64_t)gridDim.x * SC_WARPS) {
         const RecSrc X{rec + i * REC};
@@ -132,7 +133,8 @@ __device__ __forceinline__ double cl_pair_distance(int metric, double lambda, co
 __global__ void __launch_bounds__(SC_THREADS, 3)
 cl_fill_pairs(const double* rec, const double* __restrict__ ld, int64_t n, int metric, double lambda,
               int variant, double* __restrict__ M, unsigned long long* stat) {
-    __shared__ __align__(16) WarpScratch ws[SC_WARPS];
+    extern __shared__ __align__(16) unsigned char sc_smem[];
+    WarpScratch* ws = reinterpret_cast<WarpScratch*>(sc_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t npair = (n * (n - 1)) / 2;
     for (int64_t p = (int64_t)blockIdx.x * SC_WARPS + warp; p < npair; p += (int64_t)gridDim.x * SC_WARPS) {
@@ -322,7 +324,11 @@ inline size_t cl_smem_bytes(int64_t n) {
 }
 
 inline cudaError_t cluster_configure() {
-    return cudaFuncSetAttribute(cl_merge_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(cl_merge_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(cl_self_logdet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(cl_fill_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
 }
 
 }  // namespace spk

@@ -63,6 +63,7 @@ struct GwDev {                 // kernel parameters
     spkdiar_gw_window* win;
     int64_t win_cap;
     unsigned long long* nwin;  // records produced (may exceed win_cap -> E_CAPACITY)
+    unsigned long long* dbg;   // optional phase cycle counters of CTA 0: plan, eval, barrier, decide, waves, tasks
 };
 
 struct GwPlan {                // shared memory, written by thread 0
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
     int wave = 0;               // parity source for the double-buffered term arrays
     int chain_pub = 0;          // parity of the published next-chain slot
 
+    long long t_plan = 0, t_eval = 0, t_bar = 0, t_dec = 0, n_wave = 0, n_task = 0;
     int chain = group;
     while (chain < g.nchain) {
         // ---- chain state (identical in thread 0 of every CTA of the group) ----
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
 
         while (!done) {
             // ================= PLAN =================
+            const long long c0 = clock64();
             const int parity = wave & 1;
             if (threadIdx.x == 0) {
                 plan.parity = parity;
@@ -223,8 +226,11 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
             __syncthreads();
 
             // ================= EVALUATE =================
+            const long long c1 = clock64();
             const int64_t s0 = base + (int64_t)start;
-            for (int id = rank * GW_WARPS + warp; id < plan.ntask; id += gwarps) {
+            // task t -> CTA t % group_ctas, warp (t / group_ctas) % GW_WARPS: a wave with fewer
+            // tasks than warps spreads over all SMs instead of filling the first CTAs
+            for (int id = warp * g.group_ctas + rank; id < plan.ntask; id += gwarps) {
                 int64_t mm, ee;
                 int term;
                 double* dst;
@@ -260,8 +266,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                 if (KL2) {
                     Kl2Scratch& ks = reinterpret_cast<Kl2Scratch*>(scratch_base)[warp];
                     kl2_sides(WinSrc(g.st, s0, mm, REC), WinSrc(g.st, mm, ee, REC), ks, lane);
-                    seq_mean_f32(g.x, &s0, &mm, 1, lane, ks.mean[0]);
-                    seq_mean_f32(g.x, &mm, &ee, 1, lane, ks.mean[1]);
+                    seq_mean_f32(g.x, &s0, &mm, 1, lane, ks.ring, ks.mean[0]);
+                    seq_mean_f32(g.x, &mm, &ee, 1, lane, ks.ring, ks.mean[1]);
                     __syncwarp();
                     double t1, t2;
                     v = kl2_finish(ks, lane, &t1, &t2);
@@ -274,7 +280,9 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                 }
                 if (lane == 0) *dst = v;
             }
+            const long long c2 = clock64();
             gw_group_barrier(bar, bar_target, g.group_ctas);
+            const long long c3 = clock64();
             ++wave;
 
             // ================= DECIDE =================
@@ -284,6 +292,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     const int64_t e0 = (int64_t)plan.e[w];
                     const int64_t s0r = (int64_t)start;
                     const double pl = (!KL2 && g.metric == SPKDIAR_BIC) ? __ldcg(pooled + parity * GW_BMAX + w) : 0.0;
+                    const double pen = (!KL2 && g.metric == SPKDIAR_BIC) ? bic_pen(g.lambda, (double)(e0 - s0r)) : 0.0;
                     double bd = GW_NEG_INIT; int bk = -1; int ninf = 0;
                     for (int k = lane; k < plan.K[w]; k += 32) {
                         const int64_t m = (int64_t)(start + __ldg(g.T + k));
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                         const double* rp = right + (((int64_t)parity * g.bmax + w) * g.kmax + k) * rterms;
                         double d;
                         if (KL2) d = __ldcg(rp);
-                        else if (g.metric == SPKDIAR_BIC) d = bic_combine(N1, N2, __ldcg(left + k), __ldcg(rp), pl, g.lambda);
+                        else if (g.metric == SPKDIAR_BIC) d = bic_combine_pen(N1, N2, __ldcg(left + k), __ldcg(rp), pl, pen);
                         else d = glr_combine(N1, N2, __ldcg(left + k), __ldcg(rp), __ldcg(rp + 1));
                         if (d == d_inf() || d == -d_inf()) ++ninf;          // CD:219-220
                         else if (d > bd) { bd = d; bk = k; }                // CD:215-217 (strict, first wins)
@@ -308,6 +317,16 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     int kmaxw = left_valid;
+                    // negative windows ahead of the first positive one: their records take
+                    // consecutive slots claimed with ONE atomic
+                    int nneg = 0;
+                    for (int w = 0; w < plan.nW; ++w) {
+                        if (plan.bd[w] > g.threshold && plan.bk[w] >= 0) break;
+                        ++nneg;
+                        if (plan.last[w]) break;
+                    }
+                    unsigned long long slot = 0;
+                    if (rank == 0 && nneg > 0) slot = atomicAdd(g.nwin, (unsigned long long)nneg);
                     for (int w = 0; w < plan.nW; ++w) {
                         if (plan.K[w] > kmaxw) kmaxw = plan.K[w];
                         const double maxd = plan.bd[w];
@@ -322,7 +341,6 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                             break;
                         }
                         if (rank == 0) {                                                    // negative window record
-                            const unsigned long long slot = atomicAdd(g.nwin, 1ULL);
                             if ((int64_t)slot < g.win_cap) {
                                 spkdiar_gw_window r;
                                 r.start = start; r.end = plan.e[w]; r.maxi = maxi; r.maxd = maxd;
@@ -331,6 +349,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                                 r.ninf = plan.ninf[w]; r.seq = seq; r.pad = 0;
                                 g.win[slot] = r;
                             }
+                            ++slot;
                         }
                         ++seq;
                         end = plan.e_after[w]; ws = plan.ws_after[w]; dws = plan.dws_after[w];
@@ -346,13 +365,14 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     const int64_t s0r = (int64_t)start;
                     const double* f0 = fine + (int64_t)parity * 3 * GW_JMAX;
                     const double pl = plan.pend_pl;
+                    const double pen = (!KL2 && g.metric == SPKDIAR_BIC) ? bic_pen(g.lambda, (double)(e0 - s0r)) : 0.0;
                     double bd = GW_NEG_INIT; int bj = -1; int ninf = 0;
                     for (int j = lane; j < plan.nJ; j += 32) {
                         const int64_t m = (int64_t)(start + plan.fi[j]);
                         const double N1 = (double)(m - s0r), N2 = (double)(e0 - m);
                         double d;
                         if (KL2) d = __ldcg(f0 + j);
-                        else if (g.metric == SPKDIAR_BIC) d = bic_combine(N1, N2, __ldcg(f0 + j), __ldcg(f0 + GW_JMAX + j), pl, g.lambda);
+                        else if (g.metric == SPKDIAR_BIC) d = bic_combine_pen(N1, N2, __ldcg(f0 + j), __ldcg(f0 + GW_JMAX + j), pl, pen);
                         else d = glr_combine(N1, N2, __ldcg(f0 + j), __ldcg(f0 + GW_JMAX + j), __ldcg(f0 + 2 * GW_JMAX + j));
                         if (d == d_inf() || d == -d_inf()) ++ninf;
                         else if (d > bd) { bd = d; bj = j; }
@@ -403,6 +423,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
             start = plan.e_after[0];
             left_valid = plan.K[0];
             __syncthreads();
+            t_plan += c1 - c0; t_eval += c2 - c1; t_bar += c3 - c2; t_dec += clock64() - c3; ++n_wave; n_task += plan.ntask;
         }
 
         // ---- next chain for this group ----
@@ -414,6 +435,9 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
         gw_group_barrier(bar, bar_target, g.group_ctas);
         chain = *((volatile int32_t*)(g.group_chain + group * 2 + chain_pub));
         chain_pub ^= 1;
+    }
+    if (g.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+        g.dbg[0] = t_plan; g.dbg[1] = t_eval; g.dbg[2] = t_bar; g.dbg[3] = t_dec; g.dbg[4] = n_wave; g.dbg[5] = n_task;
     }
 }
 

@@ -21,11 +21,17 @@ namespace spk {
 
 constexpr int VS = 40;     // strip stride in doubles (>= D + 1, keeps 16-byte alignment)
 
-// per-warp shared-memory scratch
-struct WarpScratch {
+constexpr int REC39 = Layout<39>::REC;
+
+// per-warp shared-memory scratch of the factorisation
+struct LdlScratch {
     double v[2][VS];       // column strips, double-buffered by step parity
     double s0[VS];         // first moments of operand X
     double s1[VS];         // first moments of operand Y (GLR mix only)
+};
+// ... plus the two operand records, staged from HBM/L2 before the matrix is formed
+struct WarpScratch : LdlScratch {
+    double rec[2][REC39];
 };
 
 // ---- operand sources ----------------------------------------------------------
@@ -64,7 +70,7 @@ struct RecSrc {
     const double* p;
     __device__ __forceinline__ double operator()(int q) const { return __ldcg(p + q); }
 };
-// a cluster record staged in shared memory
+// a record already in shared memory
 struct SmemSrc {
     const double* p;
     __device__ __forceinline__ double operator()(int q) const { return p[q]; }
@@ -74,6 +80,33 @@ struct SumSrc {
     A a; B b;
     __device__ __forceinline__ double operator()(int q) const { return a(q) + b(q); }
 };
+
+// ---- staging -------------------------------------------------------------------
+// Stage one statistics record into shared memory.  This is the MEMORY phase of a
+// task: lane-strided, fully coalesced, 8 independent element loads in flight per
+// lane and almost no live registers - whereas loading straight into the 58-double
+// register tile of the factorisation left one load in flight at a time (ncu: 62 % of
+// the stall samples on the consuming DADDs, profiles/r01_win_terms_before.txt).
+template <class Src>
+__device__ __forceinline__ const double* stage_record(const Src& src, double* buf, int lane) {
+#pragma unroll 1
+    for (int q0 = 0; q0 < REC39; q0 += 32 * 8) {
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int q = q0 + 32 * u + lane;
+            t[u] = q < REC39 ? src(q) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int q = q0 + 32 * u + lane;
+            if (q < REC39) buf[q] = t[u];
+        }
+    }
+    return buf;
+}
+// a record that already sits in shared memory is used in place
+__device__ __forceinline__ const double* stage_record(const SmemSrc& src, double*, int) { return src.p; }
 
 // ---- forming the matrix to factorise, in registers --------------------------------
 // One straight-line code path for every kind of matrix (a control-flow merge of
@@ -91,7 +124,7 @@ enum { FORM_X = 0, FORM_Y = 1, FORM_POOL = 2, FORM_MIX = 3 };
 template <int D, class SrcX, class SrcY>
 __device__ __forceinline__ double form_matrix(double (&hi)[D], double (&lo)[Layout<D>::NLO > 0 ? Layout<D>::NLO : 1],
                                               int kind, const SrcX& x, const SrcY& y, double wx, double wy,
-                                              WarpScratch& w, int lane) {
+                                              LdlScratch& w, int lane) {
     using L = Layout<D>;
     const bool ux = kind != FORM_Y, uy = kind != FORM_X;
     const bool two = kind == FORM_MIX;                 // second rank-1 correction
@@ -145,7 +178,7 @@ template <int D, bool STORE, int C>
 struct LdlStep {
     using L = Layout<D>;
     static __device__ __forceinline__ void run(double (&hi)[D], double (&lo)[L::NLO > 0 ? L::NLO : 1],
-                                               WarpScratch& w, int lane, double& p0, double& p1, bool& bad,
+                                               LdlScratch& w, int lane, double& p0, double& p1, bool& bad,
                                                double* Lsm, double* pinv) {
         const int rh = D - 1 - lane;           // my hi row (valid when lane < NL)
         double* v = w.v[C & 1];
@@ -175,13 +208,13 @@ struct LdlStep {
 template <int D, bool STORE>
 struct LdlStep<D, STORE, D> {
     using L = Layout<D>;
-    static __device__ __forceinline__ void run(double (&)[D], double (&)[L::NLO > 0 ? L::NLO : 1], WarpScratch&, int,
+    static __device__ __forceinline__ void run(double (&)[D], double (&)[L::NLO > 0 ? L::NLO : 1], LdlScratch&, int,
                                                double&, double&, bool&, double*, double*) {}
 };
 
 template <int D, bool STORE>
 __device__ __forceinline__ double ldl_logdet(double (&hi)[D], double (&lo)[Layout<D>::NLO > 0 ? Layout<D>::NLO : 1],
-                                             WarpScratch& w, int lane,
+                                             LdlScratch& w, int lane,
                                              double* Lsm = nullptr, double* pinv = nullptr) {
     double p0 = 1.0, p1 = 1.0;             // pivots c == lane and c == lane + 32
     bool bad = false;

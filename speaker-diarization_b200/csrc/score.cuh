@@ -16,6 +16,7 @@ namespace spk {
 static_assert(STAT_BLOCK == 128, "WinSrc block size must equal K1_TILE");
 constexpr int SC_WARPS = 4;                 // warps per CTA in the scoring kernels
 constexpr int SC_THREADS = SC_WARPS * 32;
+constexpr size_t SC_SMEM = SC_WARPS * sizeof(WarpScratch);     // dynamic shared memory of the scoring kernels
 
 // ---- distance formulas (fp64, reference operation order) ----------------------------
 // BIC, spk-change-detection.py:95-99 / spk-clustering.py:95-99:
@@ -25,16 +26,23 @@ __host__ __device__ inline double bic_penalty(double lambda, double N) {
     const double k = (lambda * 0.5) * (p + 0.5 * p * (p + 1.0));
     return k * log(N);
 }
-__device__ __forceinline__ double bic_combine(double N1, double N2, double ld1, double ld2,
-                                              double ld, double lambda) {
+// the penalty depends on N = N1 + N2 only: one log per window, not per candidate
+__device__ __forceinline__ double bic_pen(double lambda, double N) {
+    const double p = (double)D39;
+    const double k = __dmul_rn(__dmul_rn(lambda, 0.5), __dadd_rn(p, __dmul_rn(__dmul_rn(0.5, p), p + 1.0)));
+    return __dmul_rn(k, log(N));
+}
+__device__ __forceinline__ double bic_combine_pen(double N1, double N2, double ld1, double ld2,
+                                                  double ld, double pen) {
     const double N = N1 + N2;
     const double t0 = __dmul_rn(__dmul_rn(0.5, N), ld);
     const double c1 = __dmul_rn(__dmul_rn(0.5, N1), ld1);
     const double t2 = __dmul_rn(__dmul_rn(0.5, N2), ld2);
-    double d = __dsub_rn(__dsub_rn(t0, c1), t2);
-    const double p = (double)D39;
-    const double k = __dmul_rn(__dmul_rn(lambda, 0.5), __dadd_rn(p, __dmul_rn(__dmul_rn(0.5, p), p + 1.0)));
-    return __dsub_rn(d, __dmul_rn(k, log(N)));
+    return __dsub_rn(__dsub_rn(__dsub_rn(t0, c1), t2), pen);
+}
+__device__ __forceinline__ double bic_combine(double N1, double N2, double ld1, double ld2,
+                                              double ld, double lambda) {
+    return bic_combine_pen(N1, N2, ld1, ld2, ld, bic_pen(lambda, N1 + N2));
 }
 // GLR, spk-change-detection.py:114-115:
 //   d = -(N/2) * ((N1/N)*ln|S1| + (N2/N)*ln|S2| - ln|(N1/N) S1 + (N2/N) S2|)
@@ -61,12 +69,20 @@ __device__ __forceinline__ double range_map(double v) {     // np.log(det()) ran
 template <class SrcX, class SrcY>
 __device__ __forceinline__ double logdet_term(int term, int metric, const SrcX& X, const SrcY& Y,
                                               WarpScratch& w, int lane) {
+    const int kind = term == 0 ? FORM_X : (term == 1 ? FORM_Y : (metric == SPKDIAR_BIC ? FORM_POOL : FORM_MIX));
+    // memory phase: the operand records -> shared memory
+    const double* rx = w.rec[0];
+    const double* ry = w.rec[1];
+    if (kind != FORM_Y) rx = stage_record(X, w.rec[0], lane);
+    if (kind != FORM_X) ry = stage_record(Y, w.rec[1], lane);
+    __syncwarp();
+    // compute phase
     double hi[D39];
     double lo[L39::NLO];
-    int kind = term == 0 ? FORM_X : (term == 1 ? FORM_Y : (metric == SPKDIAR_BIC ? FORM_POOL : FORM_MIX));
+    const SmemSrc sx{rx}, sy{ry};
     double wx = 1.0, wy = 1.0;
-    if (kind == FORM_MIX) glr_weights(X(L39::CNT), Y(L39::CNT), wx, wy);
-    const double n = form_matrix<D39>(hi, lo, kind, X, Y, wx, wy, w, lane);
+    if (kind == FORM_MIX) glr_weights(sx(L39::CNT), sy(L39::CNT), wx, wy);
+    const double n = form_matrix<D39>(hi, lo, kind, sx, sy, wx, wy, w, lane);
     const double lm = ldl_logdet<D39, false>(hi, lo, w, lane);
     if (kind == FORM_MIX) return range_map(lm);
     return finish_logdet(lm, n, D39);
@@ -77,7 +93,8 @@ __global__ void __launch_bounds__(SC_THREADS, 3)
 win_terms_kernel(const Stats st, const int64_t* __restrict__ a,
                  const int64_t* __restrict__ m, const int64_t* __restrict__ b,
                  int64_t ncand, int metric, double* __restrict__ terms) {
-    __shared__ __align__(16) WarpScratch ws[SC_WARPS];
+    extern __shared__ __align__(16) unsigned char sc_smem[];
+    WarpScratch* ws = reinterpret_cast<WarpScratch*>(sc_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntask = ncand * 3;
     for (int64_t id = (int64_t)blockIdx.x * SC_WARPS + warp; id < ntask; id += (int64_t)gridDim.x * SC_WARPS) {
@@ -104,40 +121,70 @@ __global__ void win_combine_kernel(const int64_t* __restrict__ a, const int64_t*
 
 // ---- KL2 (reference semantics: diagonal-only formula, float32 sequential means) ----------
 // spk-change-detection.py:124-133, SURVEY.md Q3 / Q4.
+constexpr int KL2_ROWS = 13;     // frame rows per staging buffer
+constexpr int KL2_RING = 3;      // buffers in flight
 struct Kl2Scratch {
-    WarpScratch w;
-    double Lsm[(D39 * (D39 - 1)) / 2 + 3];
+    LdlScratch w;
+    // three uses that never overlap in time: the staged operand record (until the
+    // matrix is formed), the stored factor L (factorisation + inverse), the frame-row
+    // ring of the float32 means (after both sides are done)
+    union {
+        double rec[REC];
+        double Lsm[(D39 * (D39 - 1)) / 2 + 3];
+        float  ring[KL2_RING][KL2_ROWS * D39];
+    };
     double pinv[VS];
     double dS[2][VS];      // diag(S) of side 0 / 1
     double dP[2][VS];      // diag(S^-1)
     float  mean[2][VS];    // float32 means
 };
+static_assert(sizeof(float) * KL2_RING * KL2_ROWS * D39 <= sizeof(double) * REC, "ring must fit the record buffer");
 
 // float32 sequential mean over the concatenation of `nr` frame ranges, exactly
-// as np.mean(arr, 0) accumulates a float32 matrix row by row
+// as np.mean(arr, 0) accumulates a float32 matrix row by row:
+// lane j owns dimension j (and j + 32), adds row after row with __fadd_rn, and
+// divides by the count in float32.  The adds are a serial chain by definition;
+// what can be hidden is the memory latency: rows are staged through a 3-deep
+// ring of 16-row shared-memory buffers filled by cp.async, so 48 rows are always
+// in flight.
+__device__ __forceinline__ void kl2_stage(const float* __restrict__ src, int nel, float* buf, int lane) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(buf);
+    for (int e = lane; e < nel; e += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * e), "l"(src + e) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void seq_mean_f32(const float* __restrict__ x, const int64_t* ra,
-                                             const int64_t* rb, int64_t nr, int lane, float* out) {
+                                             const int64_t* rb, int64_t nr, int lane,
+                                             float (*ring)[KL2_ROWS * D39], float* out) {
     float s0 = 0.f, s1 = 0.f;
     int64_t cnt = 0;
     const bool second = lane + 32 < D39;
     for (int64_t r = 0; r < nr; ++r) {
         const int64_t a = ra[r], b = rb[r];
+        if (b <= a) continue;
         cnt += b - a;
-        int64_t t = a;
-        for (; t + 4 <= b; t += 4) {
-            float u[4], v[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                u[k] = __ldg(x + (t + k) * D39 + lane);
-                v[k] = second ? __ldg(x + (t + k) * D39 + lane + 32) : 0.f;
+        const int64_t ntile = (b - a + KL2_ROWS - 1) / KL2_ROWS;
+        auto rows_of = [&](int64_t t) { const int64_t left = b - (a + t * KL2_ROWS); return (int)(left < KL2_ROWS ? left : KL2_ROWS); };
+        for (int64_t t = 0; t < KL2_RING - 1; ++t) {            // prologue: fill the ring
+            if (t < ntile) kl2_stage(x + (a + t * KL2_ROWS) * D39, rows_of(t) * D39, ring[t % KL2_RING], lane);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int64_t t = 0; t < ntile; ++t) {
+            const int64_t nx = t + KL2_RING - 1;
+            if (nx < ntile) kl2_stage(x + (a + nx * KL2_ROWS) * D39, rows_of(nx) * D39, ring[nx % KL2_RING], lane);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(KL2_RING - 1) : "memory");
+            __syncwarp();
+            const float* buf = ring[t % KL2_RING];
+            const int rows = rows_of(t);
+#pragma unroll 4
+            for (int q = 0; q < rows; ++q) {
+                s0 = __fadd_rn(s0, buf[q * D39 + lane]);
+                if (second) s1 = __fadd_rn(s1, buf[q * D39 + lane + 32]);
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { s0 = __fadd_rn(s0, u[k]); s1 = __fadd_rn(s1, v[k]); }
+            __syncwarp();                                        // buffer free for the stage after next
         }
-        for (; t < b; ++t) {
-            s0 = __fadd_rn(s0, __ldg(x + t * D39 + lane));
-            if (second) s1 = __fadd_rn(s1, __ldg(x + t * D39 + lane + 32));
-        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     const float fn = (float)cnt;
     out[lane] = __fdiv_rn(s0, fn);
@@ -150,7 +197,9 @@ template <class Src>
 __device__ __forceinline__ void kl2_sides(const Src& X, const Src& Y, Kl2Scratch& k, int lane) {
 #pragma unroll 1
     for (int side = 0; side < 2; ++side) {
-        const Src src = side ? Y : X;
+        const Src gsrc = side ? Y : X;
+        const SmemSrc src{stage_record(gsrc, k.rec, lane)};
+        __syncwarp();
         double hi[D39];
         double lo[L39::NLO];
         const double n = form_matrix<D39>(hi, lo, FORM_X, src, src, 1.0, 1.0, k.w, lane);
@@ -159,6 +208,7 @@ __device__ __forceinline__ void kl2_sides(const Src& X, const Src& Y, Kl2Scratch
             const double s = k.w.s0[j];
             k.dS[side][j] = (src(L39::pos_diag(j)) - s * s / n) * rn1;
         }
+        __syncwarp();                       // the record buffer becomes the factor store
         const double lm = ldl_logdet<D39, true>(hi, lo, k.w, lane, k.Lsm, k.pinv);
         double ga, gb;
         inv_diag<D39>(k.Lsm, k.pinv, lane, ga, gb);
@@ -199,8 +249,8 @@ win_kl2_kernel(const Stats st, const float* __restrict__ x,
     for (int64_t id = (int64_t)blockIdx.x * SC_WARPS + warp; id < ncand; id += (int64_t)gridDim.x * SC_WARPS) {
         const int64_t aa = a[id], mm = m[id], bb = b[id];
         kl2_sides(WinSrc(st, aa, mm, REC), WinSrc(st, mm, bb, REC), k, lane);
-        seq_mean_f32(x, &aa, &mm, 1, lane, k.mean[0]);
-        seq_mean_f32(x, &mm, &bb, 1, lane, k.mean[1]);
+        seq_mean_f32(x, &aa, &mm, 1, lane, k.ring, k.mean[0]);
+        seq_mean_f32(x, &mm, &bb, 1, lane, k.ring, k.mean[1]);
         __syncwarp();
         double t1, t2;
         const double d = kl2_finish(k, lane, &t1, &t2);
@@ -231,7 +281,8 @@ set_records_kernel(const Stats st, const int64_t* __restrict__ off,
 __global__ void __launch_bounds__(SC_THREADS, 3)
 pair_terms_kernel(const double* recX, const double* recY, int64_t npairs, int metric,
                   double* __restrict__ terms) {
-    __shared__ __align__(16) WarpScratch ws[SC_WARPS];
+    extern __shared__ __align__(16) unsigned char sc_smem[];
+    WarpScratch* ws = reinterpret_cast<WarpScratch*>(sc_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t ntask = npairs * 3;
     for (int64_t id = (int64_t)blockIdx.x * SC_WARPS + warp; id < ntask; id += (int64_t)gridDim.x * SC_WARPS) {
@@ -266,8 +317,8 @@ pair_kl2_kernel(const double* recX, const double* recY, const float* __restrict_
     Kl2Scratch& k = ks[warp];
     for (int64_t id = (int64_t)blockIdx.x * SC_WARPS + warp; id < npairs; id += (int64_t)gridDim.x * SC_WARPS) {
         kl2_sides(RecSrc{recX + id * REC}, RecSrc{recY + id * REC}, k, lane);
-        seq_mean_f32(x, a1 + off1[id], b1 + off1[id], off1[id + 1] - off1[id], lane, k.mean[0]);
-        seq_mean_f32(x, a2 + off2[id], b2 + off2[id], off2[id + 1] - off2[id], lane, k.mean[1]);
+        seq_mean_f32(x, a1 + off1[id], b1 + off1[id], off1[id + 1] - off1[id], lane, k.ring, k.mean[0]);
+        seq_mean_f32(x, a2 + off2[id], b2 + off2[id], off2[id + 1] - off2[id], lane, k.ring, k.mean[1]);
         __syncwarp();
         double t1, t2;
         const double d = kl2_finish(k, lane, &t1, &t2);

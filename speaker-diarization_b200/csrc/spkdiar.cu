@@ -8,6 +8,8 @@
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
 //        -shared -Xcompiler -fPIC -o libspkdiar.so spkdiar.cu
 #include <algorithm>
+#include <cstdlib>
+#include <limits>
 #include <new>
 #include <vector>
 
@@ -80,6 +82,8 @@ int spkdiar_create(int device, void* stream, spkdiar_ctx** out) {
                                   (int)(SC_WARPS * sizeof(Kl2Scratch)))) != cudaSuccess) goto fail;
     if ((e = cudaFuncSetAttribute(pair_kl2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(SC_WARPS * sizeof(Kl2Scratch)))) != cudaSuccess) goto fail;
+    if ((e = cudaFuncSetAttribute(win_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM)) != cudaSuccess) goto fail;
+    if ((e = cudaFuncSetAttribute(pair_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM)) != cudaSuccess) goto fail;
     if ((e = gw_configure()) != cudaSuccess) goto fail;
     if ((e = cluster_configure()) != cudaSuccess) goto fail;
     *out = c;
@@ -286,7 +290,7 @@ int spkdiar_score_windows(spkdiar_feat* f, const int64_t* a, const int64_t* m, c
                 Stats{f->P, f->C}, f->x, da, dm, db, ncand, dout.p, terms.p);
             c->launches += 1;
         } else {
-            win_terms_kernel<<<grid_for(c, 3 * ncand, SC_WARPS, 3), SC_THREADS, 0, c->stream>>>(
+            win_terms_kernel<<<grid_for(c, 3 * ncand, SC_WARPS, 3), SC_THREADS, SC_SMEM, c->stream>>>(
                 Stats{f->P, f->C}, da, dm, db, ncand, metric, terms.p);
             win_combine_kernel<<<(unsigned)((ncand + 127) / 128), 128, 0, c->stream>>>(
                 da, dm, db, ncand, metric, lambda, terms.p, dout.p);
@@ -350,7 +354,7 @@ int spkdiar_score_sets(spkdiar_feat* f, int64_t npairs,
                 recX, recY, f->x, d_off1, d_a1, d_b1, d_off2, d_a2, d_b2, npairs, dout.p, terms.p);
             c->launches += 3;
         } else {
-            pair_terms_kernel<<<grid_for(c, 3 * npairs, SC_WARPS, 3), SC_THREADS, 0, c->stream>>>(
+            pair_terms_kernel<<<grid_for(c, 3 * npairs, SC_WARPS, 3), SC_THREADS, SC_SMEM, c->stream>>>(
                 recX, recY, npairs, metric, terms.p);
             pair_combine_kernel<<<(unsigned)((npairs + 127) / 128), 128, 0, c->stream>>>(
                 recX, recY, npairs, metric, lambda, terms.p, dout.p);
