@@ -17,6 +17,7 @@ fallback: calls raise ``SpkdiarError`` when the library or a GPU is missing.
 from . import py2fmt, feacat, synth, recipe            # noqa: F401
 from . import _abi                                     # noqa: F401
 from . import change_detection, clustering, scoring    # noqa: F401
+from . import corpus                                   # noqa: F401
 from ._abi import SpkdiarError                         # noqa: F401
 
 __version__ = '0.1.0'

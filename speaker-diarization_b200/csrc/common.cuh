@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/spkdiar.h"
 #include "layout.cuh"
 
@@ -30,6 +32,10 @@ struct spkdiar_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double prof_ms[SPKDIAR_NPROF] = {0};
     int64_t prof_n[SPKDIAR_NPROF] = {0};
+    // device-memory cache: cudaMalloc / cudaFree of the multi-GB statistics arrays cost
+    // hundreds of milliseconds per recording; blocks are kept and reused by later calls
+    struct Block { void* p; size_t bytes; bool used; };
+    std::vector<Block> pool;
 };
 
 struct spkdiar_feat {
@@ -41,7 +47,8 @@ struct spkdiar_feat {
     double* P = nullptr;          // (n + 1) block-local prefix records, lane-paired layout
     double2* C = nullptr;         // (ntiles + 1) double-double block prefix records
     double* shift = nullptr;      // 40 doubles: per-file shift subtracted before accumulation
-    double* tile = nullptr;       // per-tile sums / exclusive tile prefixes
+    double* tile = nullptr;       // per-block totals
+    double2* chunk = nullptr;     // per-chunk double-double totals of the block scan
     int64_t ntiles = 0;
 };
 
@@ -83,11 +90,51 @@ struct Prof {
     }
 };
 
+// Cached device allocation.  Every API call is synchronous on return, so a block freed
+// by one call is idle by the time the next call reuses it.
+inline cudaError_t pool_alloc(spkdiar_ctx* c, size_t bytes, void** out) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    int best = -1;
+    for (int i = 0; i < (int)c->pool.size(); ++i) {
+        const spkdiar_ctx::Block& b = c->pool[i];
+        if (!b.used && b.bytes >= bytes && b.bytes <= 2 * bytes + (1u << 20) &&
+            (best < 0 || b.bytes < c->pool[best].bytes)) best = i;
+    }
+    if (best >= 0) { c->pool[best].used = true; *out = c->pool[best].p; return cudaSuccess; }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {                       // give cached blocks back and retry once
+        cudaGetLastError();
+        for (size_t i = 0; i < c->pool.size();) {
+            if (!c->pool[i].used) { cudaFree(c->pool[i].p); c->pool.erase(c->pool.begin() + i); }
+            else ++i;
+        }
+        e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    c->pool.push_back({p, bytes, true});
+    *out = p;
+    return cudaSuccess;
+}
+inline void pool_free(spkdiar_ctx* c, const void* p) {
+    if (!p) return;
+    for (auto& b : c->pool) if (b.p == p) { b.used = false; return; }
+}
+inline void pool_destroy(spkdiar_ctx* c) {
+    for (auto& b : c->pool) cudaFree(b.p);
+    c->pool.clear();
+}
+
 template <class T>
-struct DevBuf {                      // RAII device buffer
+struct DevBuf {                      // RAII device buffer from the context's cache
+    spkdiar_ctx* c = nullptr;
     T* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t count) { return cudaMalloc((void**)&p, count * sizeof(T) + 16); }
+    ~DevBuf() { if (p) pool_free(c, p); }
+    cudaError_t alloc(spkdiar_ctx* ctx, size_t count) {
+        c = ctx;
+        return pool_alloc(ctx, count * sizeof(T) + 16, (void**)&p);
+    }
 };
 
 __device__ __forceinline__ double d_nan() { return __longlong_as_double(0x7ff8000000000000LL); }

@@ -25,7 +25,7 @@
 // come from a host-built table so that non-dyadic frame rates round as in Python.
 #pragma once
 
-#include <cooperative_groups.h>
+#include <climits>
 
 #include "common.cuh"
 #include "score.cuh"
@@ -84,6 +84,8 @@ struct GwPlan {                // shared memory, written by thread 0
     int sec[GW_BMAX + 1];      // task offsets of the right sections
     double fi[GW_JMAX];        // fine offsets i_j
     double pend_pl;            // pooled term of the window waiting for its fine tune
+    long long row_lo[GW_WARPS];   // KL2: per-warp frame-row ranges of the cooperative mean pass
+    long long row_hi[GW_WARPS];
     // decision scratch
     double bd[GW_BMAX];
     int bk[GW_BMAX];
@@ -116,6 +118,77 @@ __device__ __forceinline__ int gw_count_below(const double* __restrict__ T, int6
     return (int)k;
 }
 
+// ---- KL2: float32 sequential means, streamed cooperatively by the CTA ---------------
+// np.mean(arr, 0) of the reference adds the float32 rows one after the other
+// (SURVEY.md Q4), a serial chain per candidate and per side that re-reads the whole
+// window.  The candidates one CTA evaluates in a wave are neighbours (same window,
+// offsets 0.1 s apart), so their row ranges overlap almost completely: the CTA streams
+// the rows ONCE through a 4-stage shared-memory ring (cp.async, 128 rows per stage) and
+// every warp adds the rows of its own range [ra, rb) from shared memory, lane = dimension.
+constexpr int GW_CROWS = 128;
+constexpr int GW_CSTAGES = 4;
+constexpr size_t GW_CRING_BYTES = sizeof(float) * GW_CSTAGES * GW_CROWS * D39;
+
+__device__ __forceinline__ void gw_cta_means(const float* __restrict__ x, long long ra, long long rb,
+                                             GwPlan& plan, float* cring, int warp, int lane, float* out) {
+    if (lane == 0) { plan.row_lo[warp] = ra < rb ? ra : LLONG_MAX; plan.row_hi[warp] = ra < rb ? rb : LLONG_MIN; }
+    __syncthreads();
+    long long A = LLONG_MAX, B = LLONG_MIN;
+#pragma unroll
+    for (int w = 0; w < GW_WARPS; ++w) {
+        A = plan.row_lo[w] < A ? plan.row_lo[w] : A;
+        B = plan.row_hi[w] > B ? plan.row_hi[w] : B;
+    }
+    float s0 = 0.f, s1 = 0.f;
+    const bool second = lane + 32 < D39;
+    if (A < B) {
+        const long long nst = (B - A + GW_CROWS - 1) / GW_CROWS;
+        auto issue = [&](long long i) {
+            if (i < nst) {
+                const long long r0 = A + i * GW_CROWS;
+                const long long left = B - r0;
+                const int nel = (int)(left < GW_CROWS ? left : GW_CROWS) * D39;
+                const float* src = x + r0 * D39;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(cring + (i % GW_CSTAGES) * (GW_CROWS * D39));
+                for (int e = threadIdx.x; e < nel; e += GW_THREADS)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * e), "l"(src + e) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int p = 0; p < GW_CSTAGES - 1; ++p) issue(p);
+        for (long long i = 0; i < nst; ++i) {
+            issue(i + GW_CSTAGES - 1);
+            asm volatile("cp.async.wait_group %0;" ::"n"(GW_CSTAGES - 1) : "memory");
+            __syncthreads();                                    // stage i has landed for everybody
+            const long long r0 = A + i * GW_CROWS;
+            const long long lo = ra > r0 ? ra : r0;
+            long long hi = r0 + GW_CROWS;
+            hi = rb < hi ? rb : hi;
+            const float* buf = cring + (i % GW_CSTAGES) * (GW_CROWS * D39) + lane;
+            long long r = lo;
+            for (; r + 8 <= hi; r += 8) {                       // loads first, then the serial add chain
+                float u[8], v[8];
+                const float* row = buf + (int)(r - r0) * D39;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { u[q] = row[q * D39]; v[q] = second ? row[q * D39 + 32] : 0.f; }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { s0 = __fadd_rn(s0, u[q]); s1 = __fadd_rn(s1, v[q]); }
+            }
+            for (; r < hi; ++r) {
+                const float* row = buf + (int)(r - r0) * D39;
+                s0 = __fadd_rn(s0, row[0]);
+                if (second) s1 = __fadd_rn(s1, row[32]);
+            }
+            __syncthreads();                                    // stage buffer free for a later stage
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const float fn = (float)(rb - ra);
+    out[lane] = __fdiv_rn(s0, fn);
+    if (second) out[lane + 32] = __fdiv_rn(s1, fn);
+}
+
 template <bool KL2>
 __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
     extern __shared__ __align__(16) unsigned char gw_smem[];
@@ -125,6 +198,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
     const int group = blockIdx.x / g.group_ctas;
     const int rank = blockIdx.x - group * g.group_ctas;      // CTA rank in its group
     const int gwarps = g.group_ctas * GW_WARPS;
+    const int gpairs = gwarps / 2;            // KL2: two warps (one per side) work on one candidate
     const int rterms = KL2 ? 1 : (g.metric == SPKDIAR_GLR ? 2 : 1);
     double* left = g.left + (int64_t)group * g.kmax;
     double* right = g.right + (int64_t)group * 2 * g.bmax * g.kmax * rterms;
@@ -135,7 +209,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
     int wave = 0;               // parity source for the double-buffered term arrays
     int chain_pub = 0;          // parity of the published next-chain slot
 
-    long long t_plan = 0, t_eval = 0, t_bar = 0, t_dec = 0, n_wave = 0, n_task = 0;
+    long long t_plan = 0, t_eval = 0, t_bar = 0, t_dec = 0, n_wave = 0, n_task = 0, t_e1 = 0, t_e2 = 0;
     int chain = group;
     while (chain < g.nchain) {
         // ---- chain state (identical in thread 0 of every CTA of the group) ----
@@ -207,7 +281,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     for (int w = 0; w < plan.nW; ++w) {
                         const int newl = plan.K[w] > kmaxw ? plan.K[w] - kmaxw : 0;
                         const int t = plan.K[w] * rterms + newl + ((!KL2 && g.metric == SPKDIAR_BIC) ? 1 : 0);
-                        if (w > 0 && tasks + t > gwarps) break;
+                        if (w > 0 && tasks + t > (KL2 ? gpairs : gwarps)) break;
                         tasks += t;
                         if (plan.K[w] > kmaxw) kmaxw = plan.K[w];
                         nW = w + 1;
@@ -228,57 +302,82 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
             // ================= EVALUATE =================
             const long long c1 = clock64();
             const int64_t s0 = base + (int64_t)start;
-            // task t -> CTA t % group_ctas, warp (t / group_ctas) % GW_WARPS: a wave with fewer
-            // tasks than warps spreads over all SMs instead of filling the first CTAs
-            for (int id = warp * g.group_ctas + rank; id < plan.ntask; id += gwarps) {
-                int64_t mm, ee;
-                int term;
-                double* dst;
-                if (plan.mode == 0) {
-                    const int npool = (!KL2 && g.metric == SPKDIAR_BIC) ? plan.nW : 0;
-                    if (id < plan.nL) {                         // left term of a new coarse offset
-                        const int k = plan.k0 + id;
-                        mm = base + (int64_t)(start + __ldg(g.T + k));
-                        ee = mm; term = 0; dst = left + k;
-                    } else if (id < plan.nL + npool) {          // pooled term of window w (BIC)
-                        const int w = id - plan.nL;
-                        mm = s0; ee = base + (int64_t)plan.e[w]; term = 2;
-                        dst = pooled + parity * GW_BMAX + w;
-                    } else {                                    // right (and GLR mix) terms
-                        int w = 0;
-                        while (id >= plan.sec[w + 1]) ++w;
-                        const int r = id - plan.sec[w];
-                        const int k = r / rterms, sub = r - k * rterms;
-                        mm = base + (int64_t)(start + __ldg(g.T + k));
-                        ee = base + (int64_t)plan.e[w];
-                        term = KL2 ? 3 : (sub == 0 ? 1 : 2);
-                        dst = right + (((int64_t)parity * g.bmax + w) * g.kmax + k) * rterms + sub;
-                    }
-                } else {
-                    const int per = KL2 ? 1 : (g.metric == SPKDIAR_GLR ? 3 : 2);
-                    const int j = id / per, sub = id - j * per;
-                    mm = base + (int64_t)(start + plan.fi[j]);
-                    ee = base + (int64_t)plan.e[0];
-                    term = KL2 ? 3 : sub;
-                    dst = fine + ((int64_t)parity * 3 + sub) * GW_JMAX + j;
-                }
-                double v;
+            // A wave with fewer tasks than warps spreads over all SMs instead of filling the first
+            // CTAs.  BIC / GLR: task t -> CTA t % group_ctas.  KL2: every CTA takes a CONTIGUOUS
+            // chunk of the round (neighbouring candidates) for the cooperative mean pass.
+            for (int r0 = 0; r0 < plan.ntask; r0 += (KL2 ? gpairs : gwarps)) {
+                int id;
+                bool has;
                 if (KL2) {
-                    Kl2Scratch& ks = reinterpret_cast<Kl2Scratch*>(scratch_base)[warp];
-                    kl2_sides(WinSrc(g.st, s0, mm, REC), WinSrc(g.st, mm, ee, REC), ks, lane);
-                    seq_mean_f32(g.x, &s0, &mm, 1, lane, ks.ring, ks.mean[0]);
-                    seq_mean_f32(g.x, &mm, &ee, 1, lane, ks.ring, ks.mean[1]);
-                    __syncwarp();
-                    double t1, t2;
-                    v = kl2_finish(ks, lane, &t1, &t2);
-                    __syncwarp();
+                    // two warps per candidate (left side / right side), gpairs candidates per round
+                    const int nround = plan.ntask - r0 < gpairs ? plan.ntask - r0 : gpairs;
+                    const int chunk = (nround + g.group_ctas - 1) / g.group_ctas;
+                    const int pi = warp >> 1;
+                    id = r0 + rank * chunk + pi;
+                    has = pi < chunk && rank * chunk + pi < nround;
                 } else {
+                    id = r0 + warp * g.group_ctas + rank;
+                    has = id < plan.ntask;
+                }
+                int64_t mm = s0, ee = s0;
+                int term = 0;
+                double* dst = nullptr;
+                if (has) {
+                    if (plan.mode == 0) {
+                        const int npool = (!KL2 && g.metric == SPKDIAR_BIC) ? plan.nW : 0;
+                        if (id < plan.nL) {                         // left term of a new coarse offset
+                            const int k = plan.k0 + id;
+                            mm = base + (int64_t)(start + __ldg(g.T + k));
+                            ee = mm; term = 0; dst = left + k;
+                        } else if (id < plan.nL + npool) {          // pooled term of window w (BIC)
+                            const int w = id - plan.nL;
+                            mm = s0; ee = base + (int64_t)plan.e[w]; term = 2;
+                            dst = pooled + parity * GW_BMAX + w;
+                        } else {                                    // right (and GLR mix) terms
+                            int w = 0;
+                            while (id >= plan.sec[w + 1]) ++w;
+                            const int r = id - plan.sec[w];
+                            const int k = r / rterms, sub = r - k * rterms;
+                            mm = base + (int64_t)(start + __ldg(g.T + k));
+                            ee = base + (int64_t)plan.e[w];
+                            term = KL2 ? 3 : (sub == 0 ? 1 : 2);
+                            dst = right + (((int64_t)parity * g.bmax + w) * g.kmax + k) * rterms + sub;
+                        }
+                    } else {
+                        const int per = KL2 ? 1 : (g.metric == SPKDIAR_GLR ? 3 : 2);
+                        const int j = id / per, sub = id - j * per;
+                        mm = base + (int64_t)(start + plan.fi[j]);
+                        ee = base + (int64_t)plan.e[0];
+                        term = KL2 ? 3 : sub;
+                        dst = fine + ((int64_t)parity * 3 + sub) * GW_JMAX + j;
+                    }
+                }
+                if (KL2) {
+                    Kl2Scratch* kall = reinterpret_cast<Kl2Scratch*>(scratch_base);
+                    Kl2Scratch& own = kall[warp];               // factorisation scratch of this warp
+                    Kl2Scratch& pair = kall[warp & ~1];         // results of the candidate (both sides)
+                    float* cring = reinterpret_cast<float*>(scratch_base + GW_WARPS * sizeof(Kl2Scratch));
+                    const int side = warp & 1;
+                    const long long ra = has ? (side ? mm : s0) : 0;
+                    const long long rb = has ? (side ? ee : mm) : 0;
+                    const long long k0 = clock64();
+                    if (has) kl2_side_one(WinSrc(g.st, ra, rb, REC), own, pair.dS[side], pair.dP[side], lane);
+                    const long long k1 = clock64();
+                    gw_cta_means(g.x, ra, rb, plan, cring, warp, lane, pair.mean[side]);   // ends with __syncthreads
+                    t_e1 += k1 - k0; t_e2 += clock64() - k1;
+                    if (has && side == 0) {
+                        double t1, t2;
+                        const double v = kl2_finish(pair, lane, &t1, &t2);
+                        if (lane == 0) *dst = v;
+                    }
+                    __syncthreads();                            // pair results consumed before the next round
+                } else if (has) {
                     WarpScratch& wsr = reinterpret_cast<WarpScratch*>(scratch_base)[warp];
                     const WinSrc X(g.st, s0, mm, REC);
                     const WinSrc Y(g.st, mm, ee, REC);
-                    v = logdet_term(term, g.metric, X, Y, wsr, lane);
+                    const double v = logdet_term(term, g.metric, X, Y, wsr, lane);
+                    if (lane == 0) *dst = v;
                 }
-                if (lane == 0) *dst = v;
             }
             const long long c2 = clock64();
             gw_group_barrier(bar, bar_target, g.group_ctas);
@@ -437,7 +536,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
         chain_pub ^= 1;
     }
     if (g.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
-        g.dbg[0] = t_plan; g.dbg[1] = t_eval; g.dbg[2] = t_bar; g.dbg[3] = t_dec; g.dbg[4] = n_wave; g.dbg[5] = n_task;
+        g.dbg[0] = t_plan; g.dbg[1] = t_eval; g.dbg[2] = t_bar; g.dbg[3] = t_dec; g.dbg[4] = n_wave; g.dbg[5] = n_task; g.dbg[6] = t_e1; g.dbg[7] = t_e2;
     }
 }
 
@@ -447,7 +546,7 @@ inline cudaError_t gw_configure() {
                                          (int)(plan + GW_WARPS * sizeof(WarpScratch)));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(gw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(plan + GW_WARPS * sizeof(Kl2Scratch)));
+                                (int)(plan + GW_WARPS * sizeof(Kl2Scratch) + GW_CRING_BYTES));
 }
 
 }  // namespace spk

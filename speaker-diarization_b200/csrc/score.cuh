@@ -191,33 +191,40 @@ __device__ __forceinline__ void seq_mean_f32(const float* __restrict__ x, const 
     if (second) out[lane + 32] = __fdiv_rn(s1, fn);
 }
 
-// both sides of a KL2 evaluation: diag(S), diag(S^-1) into scratch.  The loop is
-// deliberately not unrolled: one copy of the factorisation per kernel.
+// one side of a KL2 evaluation: diag(S) and diag(S^-1) of the window / cluster `gsrc`
+// into dS / dP (shared memory); `k` is the calling warp's own scratch.
+template <class Src>
+__device__ __forceinline__ void kl2_side_one(const Src& gsrc, Kl2Scratch& k, double* dS, double* dP, int lane) {
+    const SmemSrc src{stage_record(gsrc, k.rec, lane)};
+    __syncwarp();
+    double hi[D39];
+    double lo[L39::NLO];
+    const double n = form_matrix<D39>(hi, lo, FORM_X, src, src, 1.0, 1.0, k.w, lane);
+    const double rn1 = 1.0 / (n - 1.0);
+    for (int j = lane; j < D39; j += 32) {
+        const double s = k.w.s0[j];
+        dS[j] = (src(L39::pos_diag(j)) - s * s / n) * rn1;
+    }
+    __syncwarp();                       // the record buffer becomes the factor store
+    const double lm = ldl_logdet<D39, true>(hi, lo, k.w, lane, k.Lsm, k.pinv);
+    double ga, gb;
+    inv_diag<D39>(k.Lsm, k.pinv, lane, ga, gb);
+    const bool bad = !(lm == lm);
+    if (lane < L39::NL) {
+        dP[lane] = bad ? d_nan() : ga * (n - 1.0);
+        dP[D39 - 1 - lane] = bad ? d_nan() : gb * (n - 1.0);
+    }
+    __syncwarp();
+}
+
+// both sides by one warp.  The loop is deliberately not unrolled: one copy of the
+// factorisation per kernel.
 template <class Src>
 __device__ __forceinline__ void kl2_sides(const Src& X, const Src& Y, Kl2Scratch& k, int lane) {
 #pragma unroll 1
     for (int side = 0; side < 2; ++side) {
         const Src gsrc = side ? Y : X;
-        const SmemSrc src{stage_record(gsrc, k.rec, lane)};
-        __syncwarp();
-        double hi[D39];
-        double lo[L39::NLO];
-        const double n = form_matrix<D39>(hi, lo, FORM_X, src, src, 1.0, 1.0, k.w, lane);
-        const double rn1 = 1.0 / (n - 1.0);
-        for (int j = lane; j < D39; j += 32) {
-            const double s = k.w.s0[j];
-            k.dS[side][j] = (src(L39::pos_diag(j)) - s * s / n) * rn1;
-        }
-        __syncwarp();                       // the record buffer becomes the factor store
-        const double lm = ldl_logdet<D39, true>(hi, lo, k.w, lane, k.Lsm, k.pinv);
-        double ga, gb;
-        inv_diag<D39>(k.Lsm, k.pinv, lane, ga, gb);
-        const bool bad = !(lm == lm);
-        if (lane < L39::NL) {
-            k.dP[side][lane] = bad ? d_nan() : ga * (n - 1.0);
-            k.dP[side][D39 - 1 - lane] = bad ? d_nan() : gb * (n - 1.0);
-        }
-        __syncwarp();
+        kl2_side_one(gsrc, k, k.dS[side], k.dP[side], lane);
     }
 }
 

@@ -103,6 +103,7 @@ void spkdiar_destroy(spkdiar_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    pool_destroy(c);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -143,13 +144,15 @@ static int feat_alloc(spkdiar_ctx* c, int64_t n, int32_t dim, spkdiar_feat** out
     f->ctx = c; f->n = n; f->dim = dim;
     f->ntiles = (n + K1_TILE - 1) / K1_TILE;
     cudaError_t e;
-    if ((e = cudaMalloc((void**)&f->P, (size_t)(n + 1) * REC * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&f->C, (size_t)(f->ntiles + 1) * REC * sizeof(double2))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&f->shift, K1_XS * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&f->tile, (size_t)std::max<int64_t>(f->ntiles, 1) * REC * sizeof(double))) != cudaSuccess) {
-        if (f->P) cudaFree(f->P);
-        if (f->C) cudaFree(f->C);
-        if (f->shift) cudaFree(f->shift);
+    if ((e = pool_alloc(c, (size_t)(n + 1) * REC * sizeof(double), (void**)&f->P)) != cudaSuccess ||
+        (e = pool_alloc(c, (size_t)(f->ntiles + 1) * REC * sizeof(double2), (void**)&f->C)) != cudaSuccess ||
+        (e = pool_alloc(c, K1_XS * sizeof(double), (void**)&f->shift)) != cudaSuccess ||
+        (e = pool_alloc(c, (size_t)K1_CHUNKS * REC * sizeof(double2), (void**)&f->chunk)) != cudaSuccess ||
+        (e = pool_alloc(c, (size_t)std::max<int64_t>(f->ntiles, 1) * REC * sizeof(double), (void**)&f->tile)) != cudaSuccess) {
+        pool_free(c, f->P);
+        pool_free(c, f->C);
+        pool_free(c, f->shift);
+        pool_free(c, f->chunk);
         delete f;
         return set_err(c, e == cudaErrorMemoryAllocation ? SPKDIAR_E_NOMEM : SPKDIAR_E_CUDA,
                        "device allocation for %lld frames failed: %s", (long long)n, cudaGetErrorString(e));
@@ -170,8 +173,9 @@ int spkdiar_stats_build(spkdiar_feat* f) {
         } else {
             k1_shift<<<1, 1024, 0, c->stream>>>(f->x, f->n, f->shift);
             k1_tile_write<<<(unsigned)f->ntiles, K1_THREADS, 0, c->stream>>>(f->x, f->n, f->shift, f->tile, f->P);
-            k1_tile_scan<<<(REC + 127) / 128, 128, 0, c->stream>>>(f->tile, f->ntiles, f->C);
-            c->launches += 3;
+            k1_chunk_sums<<<(K1_CHUNKS * REC + 127) / 128, 128, 0, c->stream>>>(f->tile, f->ntiles, f->chunk);
+            k1_chunk_scan<<<(K1_CHUNKS * REC + 127) / 128, 128, 0, c->stream>>>(f->tile, f->ntiles, f->chunk, f->C);
+            c->launches += 4;
         }
     }
     SPK_CUDA(c, cudaGetLastError());
@@ -185,7 +189,7 @@ int spkdiar_features_upload(spkdiar_ctx* c, const float* frames, int64_t n, int3
     if (rc) return rc;
     spkdiar_feat* f = *out;
     float* dx = nullptr;
-    cudaError_t e = cudaMalloc((void**)&dx, (size_t)std::max<int64_t>(n, 1) * dim * sizeof(float));
+    cudaError_t e = pool_alloc(c, (size_t)std::max<int64_t>(n, 1) * dim * sizeof(float), (void**)&dx);
     if (e != cudaSuccess) {
         spkdiar_features_free(f); *out = nullptr;
         return set_err(c, SPKDIAR_E_NOMEM, "device allocation for the frames failed: %s", cudaGetErrorString(e));
@@ -218,11 +222,12 @@ int spkdiar_features_free(spkdiar_feat* f) {
     if (!f) return SPKDIAR_OK;
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
-    if (f->P) cudaFree(f->P);
-    if (f->C) cudaFree(f->C);
-    if (f->shift) cudaFree(f->shift);
-    if (f->tile) cudaFree(f->tile);
-    if (f->own_x && f->x) cudaFree(const_cast<float*>(f->x));
+    pool_free(f->ctx, f->P);
+    pool_free(f->ctx, f->C);
+    pool_free(f->ctx, f->shift);
+    pool_free(f->ctx, f->chunk);
+    pool_free(f->ctx, f->tile);
+    if (f->own_x) pool_free(f->ctx, f->x);
     delete f;
     return SPKDIAR_OK;
 }
@@ -275,9 +280,9 @@ int spkdiar_score_windows(spkdiar_feat* f, const int64_t* a, const int64_t* m, c
                            (long long)a[k], (long long)m[k], (long long)b[k], (long long)f->n);
     SPK_CUDA(c, cudaSetDevice(c->device));
     DevBuf<int64_t> idx; DevBuf<double> terms, dout;
-    SPK_CUDA(c, idx.alloc(3 * ncand));
-    SPK_CUDA(c, terms.alloc(3 * ncand));
-    SPK_CUDA(c, dout.alloc(ncand));
+    SPK_CUDA(c, idx.alloc(c, 3 * ncand));
+    SPK_CUDA(c, terms.alloc(c, 3 * ncand));
+    SPK_CUDA(c, dout.alloc(c, ncand));
     int64_t *da = idx.p, *dm = idx.p + ncand, *db = idx.p + 2 * ncand;
     const size_t nb = ncand * sizeof(int64_t);
     SPK_CUDA(c, cudaMemcpyAsync(da, a, nb, cudaMemcpyHostToDevice, c->stream));
@@ -327,10 +332,10 @@ int spkdiar_score_sets(spkdiar_feat* f, int64_t npairs,
     SPK_CUDA(c, cudaSetDevice(c->device));
     DevBuf<int64_t> idx; DevBuf<double> rec, terms, dout;
     const int64_t nidx = 2 * (npairs + 1) + 2 * nr1 + 2 * nr2;
-    SPK_CUDA(c, idx.alloc(nidx));
-    SPK_CUDA(c, rec.alloc(2 * npairs * REC));
-    SPK_CUDA(c, terms.alloc(3 * npairs));
-    SPK_CUDA(c, dout.alloc(npairs));
+    SPK_CUDA(c, idx.alloc(c, nidx));
+    SPK_CUDA(c, rec.alloc(c, 2 * npairs * REC));
+    SPK_CUDA(c, terms.alloc(c, 3 * npairs));
+    SPK_CUDA(c, dout.alloc(c, npairs));
     int64_t* d_off1 = idx.p; int64_t* d_off2 = d_off1 + npairs + 1;
     int64_t* d_a1 = d_off2 + npairs + 1; int64_t* d_b1 = d_a1 + nr1;
     int64_t* d_a2 = d_b1 + nr1; int64_t* d_b2 = d_a2 + nr2;

@@ -29,9 +29,9 @@
 // Frames are centred on a per-file shift vector first (covariances are shift
 // invariant; centring keeps even the in-block cancellation small).
 //
-// Two launches, bit-reproducible run to run:
+// Three launches, bit-reproducible run to run:
 //   tile_write  one CTA per block: running sums written per frame + block total
-//   tile_scan   double-double exclusive scan of the block totals, one thread per component
+//   chunk_sums / chunk_scan  double-double exclusive scan of the block totals
 // Algorithmic traffic per frame: 156 B read + 6,560 B written (HBM-bound); the
 // block level adds 13,120 B per 128 frames (+1.6 %).
 #pragma once
@@ -112,42 +112,69 @@ __device__ __forceinline__ void k1_load_tile(const float* __restrict__ x, int64_
     __syncthreads();
 }
 
-// exclusive double-double scan over the block totals, one thread per component,
-// fixed left-to-right order.  C[j] = sum of totals of blocks < j.
-__global__ void __launch_bounds__(128) k1_tile_scan(const double* __restrict__ tile, int64_t ntiles,
-                                                    double2* __restrict__ C) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= REC) return;
+// ---- exclusive double-double scan over the block totals ------------------------------
+// C[j] = sum of the totals of blocks < j, per component, as (hi, lo).  The blocks are cut
+// into K1_CHUNKS contiguous chunks; thread (chunk, component) first sums its chunk, then
+// adds the totals of the chunks before it IN ORDER and rescans its chunk.  The association
+// is fixed by the block count alone, so the result is bit-reproducible, and consecutive
+// threads own consecutive components, so every access is coalesced.
+constexpr int K1_CHUNKS = 64;
+
+__device__ __forceinline__ void dd_add(double& hi, double& lo, double v) {       // (hi, lo) += v
+    const double s = __dadd_rn(hi, v);                         // TwoSum(hi, v)
+    const double bb = __dsub_rn(s, hi);
+    const double err = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(v, bb));
+    lo = __dadd_rn(lo, err);
+    const double h2 = __dadd_rn(s, lo);                        // renormalise (FastTwoSum)
+    lo = __dsub_rn(lo, __dsub_rn(h2, s));
+    hi = h2;
+}
+
+__global__ void __launch_bounds__(128) k1_chunk_sums(const double* __restrict__ tile, int64_t ntiles,
+                                                     double2* __restrict__ chunk_tot) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K1_CHUNKS * REC) return;
+    const int ch = idx / REC, q = idx - ch * REC;
+    const int64_t per = (ntiles + K1_CHUNKS - 1) / K1_CHUNKS;
+    const int64_t t0 = ch * per, t1 = (t0 + per < ntiles) ? t0 + per : ntiles;
     double hi = 0.0, lo = 0.0;
-    int64_t t = 0;
-    for (; t + 8 <= ntiles; t += 8) {
+    int64_t t = t0;
+    for (; t + 8 <= t1; t += 8) {
         double v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) v[u] = tile[(t + u) * REC + q];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            C[(t + u) * REC + q] = make_double2(hi, lo);
-            const double s = __dadd_rn(hi, v[u]);                 // TwoSum(hi, v)
-            const double bb = __dsub_rn(s, hi);
-            const double err = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(v[u], bb));
-            lo = __dadd_rn(lo, err);
-            const double h2 = __dadd_rn(s, lo);                    // renormalise (FastTwoSum)
-            lo = __dsub_rn(lo, __dsub_rn(h2, s));
-            hi = h2;
-        }
+        for (int u = 0; u < 8; ++u) dd_add(hi, lo, v[u]);
     }
-    for (; t < ntiles; ++t) {
-        const double v = tile[t * REC + q];
-        C[t * REC + q] = make_double2(hi, lo);
-        const double s = __dadd_rn(hi, v);
-        const double bb = __dsub_rn(s, hi);
-        const double err = __dadd_rn(__dsub_rn(hi, __dsub_rn(s, bb)), __dsub_rn(v, bb));
-        lo = __dadd_rn(lo, err);
-        const double h2 = __dadd_rn(s, lo);
-        lo = __dsub_rn(lo, __dsub_rn(h2, s));
-        hi = h2;
+    for (; t < t1; ++t) dd_add(hi, lo, tile[t * REC + q]);
+    chunk_tot[idx] = make_double2(hi, lo);
+}
+
+__global__ void __launch_bounds__(128) k1_chunk_scan(const double* __restrict__ tile, int64_t ntiles,
+                                                     const double2* __restrict__ chunk_tot,
+                                                     double2* __restrict__ C) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K1_CHUNKS * REC) return;
+    const int ch = idx / REC, q = idx - ch * REC;
+    const int64_t per = (ntiles + K1_CHUNKS - 1) / K1_CHUNKS;
+    const int64_t t0 = ch * per, t1 = (t0 + per < ntiles) ? t0 + per : ntiles;
+    double hi = 0.0, lo = 0.0;
+    for (int c = 0; c < ch; ++c) {                             // totals of the chunks before mine, in order
+        const double2 v = chunk_tot[c * REC + q];
+        dd_add(hi, lo, v.x);
+        dd_add(hi, lo, v.y);
     }
-    C[ntiles * REC + q] = make_double2(hi, lo);
+    int64_t t = t0;
+    for (; t + 8 <= t1; t += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = tile[(t + u) * REC + q];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { C[(t + u) * REC + q] = make_double2(hi, lo); dd_add(hi, lo, v[u]); }
+    }
+    for (; t < t1; ++t) { C[t * REC + q] = make_double2(hi, lo); dd_add(hi, lo, tile[t * REC + q]); }
+    // the thread that owns the last block also writes the grand total
+    if (t1 == ntiles && t0 < ntiles) C[ntiles * REC + q] = make_double2(hi, lo);
 }
 
 // one CTA per block of K1_TILE frames: P[f0] = 0, P[f0 + t + 1] = running sums

@@ -214,3 +214,25 @@ def test_scoring_tools_agree_on_gpu_and_oracle_outputs(tmp_path, ctx):
                      b.getvalue().replace(clu, 'CLU'))
     assert outs['o'] == outs['p']
     assert 'DER:' in outs['p'][3]
+
+
+def test_corpus_driver_equals_per_file_scripts(tmp_path, ctx):
+    """One resident context streaming several recordings == running the two
+    drop-in scripts once per file (spk-diarization2.py:122-128)."""
+    from spkdiar import corpus
+    items = []
+    for k in range(4):
+        rec = synth.make_recording(600 + k, 5000 + 700 * k, 2 + k % 3)
+        lines = synth.one_line_recipe('/syn/r%d.wav' % k, rec)
+        items.append(('r%d' % k, lines, rec.frames))
+        synth.write_case(str(tmp_path), 'r%d' % k, rec, lines)
+    summ = corpus.run_corpus(items, 0, 1, device=0, outdir=str(tmp_path / 'out'), frame_rate=100)
+    assert set(summ) == {'r0', 'r1', 'r2', 'r3'}
+    for k in range(4):
+        seg, clu = str(tmp_path / ('s%d.recipe' % k)), str(tmp_path / ('c%d.recipe' % k))
+        run_product('cd', 0, [str(tmp_path / ('r%d.recipe' % k)), str(tmp_path / 'fea'), '-o', seg, '-f', '100']
+                    + cases.D2_GW, ctx)
+        run_product('cl', 1, [seg, str(tmp_path / 'fea'), '-o', clu, '-f', '100', '-m', 'hi', '-l', '1.3'], ctx)
+        assert open(seg).read() == open(str(tmp_path / 'out' / ('r%d.spkc.recipe' % k))).read()
+        assert open(clu).read() == open(str(tmp_path / 'out' / ('r%d.recipe' % k))).read()
+        assert summ['r%d' % k]['speakers'] >= 1
