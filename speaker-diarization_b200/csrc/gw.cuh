@@ -23,12 +23,27 @@
 // IEEE fp64 in the reference's operation order; frame indices are truncations
 // of those doubles.  Candidate offsets T[k] = fl(T[k-1] + istep)
 // come from a host-built table so that non-dyadic frame rates round as in Python.
+//
+// KL2 (spk-change-detection.py:124-133) needs, besides diag(S) and diag(S^-1) of
+// both sides, the reference's float32 means: np.mean adds the float32 rows of the
+// slice one after the other, so a mean is a serial chain of fp32
+// additions that depends on where the slice STARTS.  While `start` does not move
+//   - all left means [start, m_k) are snapshots of ONE running sum from `start`;
+//   - the right sum [m_k, end) of candidate k is a running sum from m_k that only
+//     has to be EXTENDED when `end` grows;
+// so the kernel keeps one running sum per candidate offset ("sum chain") alive in
+// HBM across windows and waves, and a wave only adds the new rows.  The rows are
+// streamed through a shared-memory ring filled by bulk asynchronous copies (TMA),
+// twelve chains (one per warp) sharing one stream per CTA.  Left
+// sides are cached per offset exactly like the left BIC term.  A KL2 wave has two
+// steps separated by a group barrier: sides + sums, then the distances.
 #pragma once
 
 #include <climits>
 
 #include "common.cuh"
 #include "score.cuh"
+#include "tma.cuh"
 
 namespace spk {
 
@@ -38,9 +53,15 @@ constexpr int GW_BMAX = GW_WARPS;       // windows per speculative batch (one de
 constexpr int GW_JMAX = 128;            // fine-tune candidates (2*istep + 1 <= JMAX)
 #define GW_NEG_INIT (-9223372036854775808.0)   /* -sys.maxint - 1 as a double, CD:203 */
 
+constexpr int KS = 2 * VS;              // doubles per cached KL2 side: diag(S)[40], diag(S^-1)[40]
+constexpr int GW_RING_ROWS = 64;        // frame rows per ring stage (a multiple of 4: 16-byte spans)
+constexpr int GW_RING_STAGES = 6;
+constexpr int GW_STAGE_FLOATS = GW_RING_ROWS * D39;
+
 struct GwDev {                 // kernel parameters
     Stats st;                  // two-level frame statistics
     const float* x;            // frames (KL2 means)
+    int64_t nrows;             // frames in the recording
     const double* T;           // candidate offset table, kmax entries
     int64_t kmax;
     const int64_t* seg_a;      // chains
@@ -56,6 +77,14 @@ struct GwDev {                 // kernel parameters
     double* right;             // [ngroups][2 parity][bmax][kmax][rterms]
     double* pooled;            // [ngroups][2 parity][GW_BMAX]
     double* fine;              // [ngroups][2 parity][3][GW_JMAX]
+    // KL2 workspaces, per group
+    int64_t kcap;              // candidate slots per parity
+    double* kside_left;        // [ngroups][kmax][KS]
+    double* kside_right;       // [ngroups][2][kcap][KS]
+    double* kside_fine;        // [ngroups][2][2 sides][GW_JMAX][KS]
+    float* ksum_left;          // [ngroups][kmax][VS]      running sum of [start, m_k)
+    float* ksum_right;         // [ngroups][2][kcap][VS]   running sum of [m_k, end_w)
+    float* ksum_fine;          // [ngroups][2][2 sides][GW_JMAX][VS]
     unsigned long long* bar;   // [ngroups] barrier counters
     int32_t* next_chain;       // queue cursor
     int32_t* group_chain;      // [ngroups][2] published next chain per group
@@ -75,21 +104,36 @@ struct GwPlan {                // shared memory, written by thread 0
     int parity;
     int nJ;                    // fine candidates
     int rterms;
+    int kmaxw;                 // largest candidate count of the batch
+    int pend_bk;               // coarse maximum of the window waiting for its fine tune
+    // KL2 sum chains that survive from the previous coarse wave of the same `start`
+    int chain_valid;           // offsets k < chain_valid have a running right sum ...
+    int chain_base;            // ... in slot chain_base + k of parity chain_parity ...
+    int chain_parity;
+    long long chain_row;       // ... that ends at this frame row
     double e[GW_BMAX];         // window ends
     double ws_after[GW_BMAX];  // growth state after a negative window w
     double dws_after[GW_BMAX];
     double e_after[GW_BMAX];
     int last[GW_BMAX];         // a negative window w ends the chain
     int K[GW_BMAX];            // coarse candidates of window w
-    int sec[GW_BMAX + 1];      // task offsets of the right sections
+    int sec[GW_BMAX + 1];      // BIC/GLR: task offsets of the right sections; KL2: candidate slot offsets
     double fi[GW_JMAX];        // fine offsets i_j
     double pend_pl;            // pooled term of the window waiting for its fine tune
-    long long row_lo[GW_WARPS];   // KL2: per-warp frame-row ranges of the cooperative mean pass
-    long long row_hi[GW_WARPS];
     // decision scratch
     double bd[GW_BMAX];
     int bk[GW_BMAX];
     int ninf[GW_BMAX];
+};
+
+// per-warp factorisation scratch of the KL2 kernel
+struct GwKl2Warp {
+    LdlScratch w;
+    union {
+        double rec[REC];
+        double Lsm[(D39 * (D39 - 1)) / 2 + 3];
+    };
+    double pinv[VS];
 };
 
 __device__ __forceinline__ void gw_group_barrier(unsigned long long* ctr, unsigned long long& target,
@@ -118,75 +162,233 @@ __device__ __forceinline__ int gw_count_below(const double* __restrict__ T, int6
     return (int)k;
 }
 
-// ---- KL2: float32 sequential means, streamed cooperatively by the CTA ---------------
-// np.mean(arr, 0) of the reference adds the float32 rows one after the other
-// (SURVEY.md Q4), a serial chain per candidate and per side that re-reads the whole
-// window.  The candidates one CTA evaluates in a wave are neighbours (same window,
-// offsets 0.1 s apart), so their row ranges overlap almost completely: the CTA streams
-// the rows ONCE through a 4-stage shared-memory ring (cp.async, 128 rows per stage) and
-// every warp adds the rows of its own range [ra, rb) from shared memory, lane = dimension.
-constexpr int GW_CROWS = 128;
-constexpr int GW_CSTAGES = 4;
-constexpr size_t GW_CRING_BYTES = sizeof(float) * GW_CSTAGES * GW_CROWS * D39;
+// ---- KL2: sum chains ---------------------------------------------------------------------
+// One chain = one float32 running sum over consecutive frame rows, lane j owning
+// dimensions j and j + 32, with SNAPSHOTS of the sum stored at given rows.
+//   kind 0  coarse right chain of offset k = a: rows from m_k (or from where the previous
+//           wave stopped) up to the end of every window w >= w0 of the batch
+//   kind 1  coarse left chain: continues the running sum of [start, .) through the new offsets
+//   kind 2  fine right chain of fine candidate j = a: rows [m_j, end)
+//   kind 3  fine left chain: from the nearest cached coarse offset through the fine offsets
+// Chain ct of a wave belongs to CTA ct % group_ctas; a CTA runs its chains twelve at a time,
+// one per warp, over ONE stream of rows: thread 0 feeds a shared-memory ring with bulk copies
+// (TMA) of GW_RING_ROWS rows, every warp adds the rows of its own range from the ring.
+struct GwChain { int kind, a, w0, nsnap; long long pos; const float* init; };
 
-__device__ __forceinline__ void gw_cta_means(const float* __restrict__ x, long long ra, long long rb,
-                                             GwPlan& plan, float* cring, int warp, int lane, float* out) {
-    if (lane == 0) { plan.row_lo[warp] = ra < rb ? ra : LLONG_MAX; plan.row_hi[warp] = ra < rb ? rb : LLONG_MIN; }
+struct GwChainCtx {
+    const GwDev* g; const GwPlan* plan;
+    int64_t base; double start;
+    float* sum_left; float* sum_right; float* sum_fine;     // this group's arrays
+};
+
+__device__ __forceinline__ long long gw_snap_row(const GwChainCtx& c, const GwChain& ch, int i) {
+    switch (ch.kind) {
+        case 0:  return c.base + (int64_t)c.plan->e[ch.w0 + i];
+        case 1:  return c.base + (int64_t)(c.start + __ldg(c.g->T + c.plan->k0 + i));
+        case 2:  return c.base + (int64_t)c.plan->e[0];
+        default: return c.base + (int64_t)(c.start + c.plan->fi[i]);
+    }
+}
+__device__ __forceinline__ float* gw_snap_dst(const GwChainCtx& c, const GwChain& ch, int i) {
+    const int parity = c.plan->parity;
+    switch (ch.kind) {
+        case 0:  return c.sum_right + ((int64_t)parity * c.g->kcap + c.plan->sec[ch.w0 + i] + ch.a) * VS;
+        case 1:  return c.sum_left + (int64_t)(c.plan->k0 + i) * VS;
+        case 2:  return c.sum_fine + ((int64_t)(parity * 2 + 1) * GW_JMAX + ch.a) * VS;
+        default: return c.sum_fine + ((int64_t)(parity * 2 + 0) * GW_JMAX + i) * VS;
+    }
+}
+
+// One round of the sum pass: every warp of the CTA runs (at most) one chain.  `range` is
+// a shared-memory scratch of 2 * GW_WARPS long longs, `phase` the mbarrier phase bit of
+// every ring stage (identical in all threads, lives as long as the kernel).
+__device__ __forceinline__ void gw_sum_round(const GwChainCtx& c, const GwChain& ch, bool active,
+                                             long long* range, float* ring, uint64_t* bars, uint32_t& phase,
+                                             int warp, int lane, long long& dbg_rows, long long& dbg_wait) {
+    const float* __restrict__ x = c.g->x;
+    const bool second = lane + 32 < D39;
+    float s0 = 0.f, s1 = 0.f;
+    int si = 0;
+    // the left chain takes a snapshot at every new offset: the offsets T[k0 + i] are fetched 32 at a
+    // time (one coalesced load per 32 snapshots instead of one dependent L2 round trip per snapshot)
+    int tb = -1;
+    double tc = 0.0;
+    auto snap_row = [&](int i) -> long long {
+        if (ch.kind != 1) return gw_snap_row(c, ch, i);
+        if ((i >> 5) != tb) {
+            tb = i >> 5;
+            const int64_t k = (int64_t)c.plan->k0 + 32 * tb + lane;
+            tc = k < c.g->kmax ? __ldg(c.g->T + k) : 0.0;
+        }
+        return c.base + (int64_t)(c.start + __shfl_sync(0xffffffffu, tc, i & 31));
+    };
+    long long snap_abs = LLONG_MAX, rb_abs = 0;
+    auto store_snap = [&]() {
+        float* dst = gw_snap_dst(c, ch, si);
+        dst[lane] = s0;
+        if (second) dst[lane + 32] = s1;
+        ++si;
+        snap_abs = si < ch.nsnap ? snap_row(si) : LLONG_MAX;
+    };
+    if (active) {
+        if (ch.init) {                               // written by another CTA one wave ago: L2
+            s0 = __ldcg(ch.init + lane);
+            if (second) s1 = __ldcg(ch.init + 32 + lane);
+        }
+        rb_abs = snap_row(ch.nsnap - 1);             // last row + 1
+        snap_abs = snap_row(0);
+        while (si < ch.nsnap && snap_abs <= ch.pos) store_snap();
+        if (si >= ch.nsnap) active = false;
+    }
+    if (lane == 0) {
+        range[2 * warp] = active ? ch.pos : LLONG_MAX;
+        range[2 * warp + 1] = active ? rb_abs : LLONG_MIN;
+    }
     __syncthreads();
     long long A = LLONG_MAX, B = LLONG_MIN;
 #pragma unroll
     for (int w = 0; w < GW_WARPS; ++w) {
-        A = plan.row_lo[w] < A ? plan.row_lo[w] : A;
-        B = plan.row_hi[w] > B ? plan.row_hi[w] : B;
+        A = range[2 * w] < A ? range[2 * w] : A;
+        B = range[2 * w + 1] > B ? range[2 * w + 1] : B;
     }
-    float s0 = 0.f, s1 = 0.f;
-    const bool second = lane + 32 < D39;
-    if (A < B) {
-        const long long nst = (B - A + GW_CROWS - 1) / GW_CROWS;
-        auto issue = [&](long long i) {
-            if (i < nst) {
-                const long long r0 = A + i * GW_CROWS;
-                const long long left = B - r0;
-                const int nel = (int)(left < GW_CROWS ? left : GW_CROWS) * D39;
-                const float* src = x + r0 * D39;
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(cring + (i % GW_CSTAGES) * (GW_CROWS * D39));
-                for (int e = threadIdx.x; e < nel; e += GW_THREADS)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * e), "l"(src + e) : "memory");
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        for (int p = 0; p < GW_CSTAGES - 1; ++p) issue(p);
-        for (long long i = 0; i < nst; ++i) {
-            issue(i + GW_CSTAGES - 1);
-            asm volatile("cp.async.wait_group %0;" ::"n"(GW_CSTAGES - 1) : "memory");
-            __syncthreads();                                    // stage i has landed for everybody
-            const long long r0 = A + i * GW_CROWS;
-            const long long lo = ra > r0 ? ra : r0;
-            long long hi = r0 + GW_CROWS;
-            hi = rb < hi ? rb : hi;
-            const float* buf = cring + (i % GW_CSTAGES) * (GW_CROWS * D39) + lane;
-            long long r = lo;
-            for (; r + 8 <= hi; r += 8) {                       // loads first, then the serial add chain
-                float u[8], v[8];
-                const float* row = buf + (int)(r - r0) * D39;
+    __syncthreads();                                 // `range` may be rewritten by the next round
+    if (!(A < B)) return;
+    A &= ~3LL;                                       // 16-byte aligned start of the stream
+    const int nst = (int)((B - A + GW_RING_ROWS - 1) / GW_RING_ROWS);
+    const long long file_bytes = c.g->nrows * (long long)(D39 * sizeof(float));
+    auto stage_bytes = [&](int i) {
+        long long nb = file_bytes - (A + (long long)i * GW_RING_ROWS) * (long long)(D39 * sizeof(float));
+        if (nb > (long long)(GW_STAGE_FLOATS * sizeof(float))) nb = GW_STAGE_FLOATS * sizeof(float);
+        return (unsigned)(nb & ~15LL);
+    };
+    auto issue = [&](int i) {                        // thread 0 only
+        const int s = i % GW_RING_STAGES;
+        const unsigned nb = stage_bytes(i);
+        mbar_expect_tx(bars + s, nb);
+        bulk_g2s(ring + s * GW_STAGE_FLOATS, x + (A + (long long)i * GW_RING_ROWS) * D39, nb, bars + s);
+    };
+    if (threadIdx.x == 0)
+        for (int p = 0; p < GW_RING_STAGES && p < nst; ++p) issue(p);
+    // positions relative to A from here on (a batch spans far less than 2^31 rows)
+    int pos = active ? (int)(ch.pos - A) : 0;
+    const int rb = active ? (int)(rb_abs - A) : 0;
+    int snap = active ? (int)(snap_abs - A) : INT_MAX;
+    if (active) dbg_rows += rb - pos;
+    for (int i = 0; i < nst; ++i) {
+        const int s = i % GW_RING_STAGES;
+        const long long w0c = clock64();
+        mbar_wait(bars + s, (phase >> s) & 1u);
+        phase ^= 1u << s;
+        dbg_wait += clock64() - w0c;
+        const int r0 = i * GW_RING_ROWS;
+        int hi = r0 + GW_RING_ROWS;
+        hi = rb < hi ? rb : hi;
+        if (active && pos < hi) {
+            const int safe = r0 + (int)(stage_bytes(i) / (D39 * sizeof(float)));     // rows fully in the ring
+            const float* buf = ring + s * GW_STAGE_FLOATS + lane - r0 * D39;         // buf[r * D39] = row r
+            int r = pos > r0 ? pos : r0;
+            for (;;) {
+                if (r == snap) {                                 // the sum of the rows below `snap`
+                    store_snap();
+                    snap = snap_abs == LLONG_MAX ? INT_MAX : (int)(snap_abs - A);
+                    continue;
+                }
+                if (r >= hi) break;
+                const int seg = snap < hi ? snap : hi;
+                const int sseg = seg < safe ? seg : safe;
+                for (; r + 8 <= sseg; r += 8) {                  // loads first, then the serial add chain
+                    float u[8], v[8];
+                    const float* row = buf + r * D39;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { u[q] = row[q * D39]; v[q] = second ? row[q * D39 + 32] : 0.f; }
+                    for (int q = 0; q < 8; ++q) { u[q] = row[q * D39]; v[q] = second ? row[q * D39 + 32] : 0.f; }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { s0 = __fadd_rn(s0, u[q]); s1 = __fadd_rn(s1, v[q]); }
+                    for (int q = 0; q < 8; ++q) { s0 = __fadd_rn(s0, u[q]); s1 = __fadd_rn(s1, v[q]); }
+                }
+                for (; r < sseg; ++r) {
+                    s0 = __fadd_rn(s0, buf[r * D39]);
+                    if (second) s1 = __fadd_rn(s1, buf[r * D39 + 32]);
+                }
+                for (; r < seg; ++r) {                           // the last rows of the file: not 16-byte copyable
+                    const float* row = x + (A + r) * D39 + lane;
+                    s0 = __fadd_rn(s0, __ldg(row));
+                    if (second) s1 = __fadd_rn(s1, __ldg(row + 32));
+                }
             }
-            for (; r < hi; ++r) {
-                const float* row = buf + (int)(r - r0) * D39;
-                s0 = __fadd_rn(s0, row[0]);
-                if (second) s1 = __fadd_rn(s1, row[32]);
-            }
-            __syncthreads();                                    // stage buffer free for a later stage
+            pos = hi;
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                         // stage i has been consumed by every warp
+        if (threadIdx.x == 0 && i + GW_RING_STAGES < nst) issue(i + GW_RING_STAGES);
     }
-    __syncthreads();
-    const float fn = (float)(rb - ra);
-    out[lane] = __fdiv_rn(s0, fn);
-    if (second) out[lane + 32] = __fdiv_rn(s1, fn);
+}
+
+// chain ct of the current wave (see the kinds above)
+__device__ __forceinline__ GwChain gw_make_chain(const GwChainCtx& c, int ct, int nright, int left_valid,
+                                                 int64_t s0) {
+    const GwDev& g = *c.g;
+    const GwPlan& plan = *c.plan;
+    GwChain ch;
+    if (plan.mode == 0 && ct < nright) {                   // coarse right chain of offset k
+        const int k = ct;
+        ch.kind = 0; ch.a = k;
+        int w0 = 0;
+        while (w0 < plan.nW && plan.K[w0] <= k) ++w0;
+        ch.w0 = w0; ch.nsnap = plan.nW - w0;
+        if (k < plan.chain_valid) {
+            ch.pos = plan.chain_row;
+            ch.init = c.sum_right + ((int64_t)plan.chain_parity * g.kcap + plan.chain_base + k) * VS;
+        } else {
+            ch.pos = c.base + (int64_t)(c.start + __ldg(g.T + k));
+            ch.init = nullptr;
+        }
+    } else if (plan.mode == 0) {                            // coarse left chain
+        ch.kind = 1; ch.a = 0; ch.w0 = 0; ch.nsnap = plan.nL;
+        if (plan.k0 > 0) {
+            ch.pos = c.base + (int64_t)(c.start + __ldg(g.T + plan.k0 - 1));
+            ch.init = c.sum_left + (int64_t)(plan.k0 - 1) * VS;
+        } else {
+            ch.pos = s0; ch.init = nullptr;
+        }
+    } else if (ct < nright) {                               // fine right chain
+        ch.kind = 2; ch.a = ct; ch.w0 = 0; ch.nsnap = 1;
+        ch.pos = c.base + (int64_t)(c.start + plan.fi[ct]);
+        ch.init = nullptr;
+    } else {                                                // fine left chain
+        ch.kind = 3; ch.a = 0; ch.w0 = 0; ch.nsnap = plan.nJ;
+        const long long m0 = c.base + (int64_t)(c.start + plan.fi[0]);
+        int kk = plan.pend_bk - 1;                          // nearest cached offset at or below m0
+        if (kk >= left_valid) kk = left_valid - 1;
+        while (kk + 1 < left_valid && c.base + (int64_t)(c.start + __ldg(g.T + kk + 1)) <= m0) ++kk;
+        while (kk >= 0 && c.base + (int64_t)(c.start + __ldg(g.T + kk)) > m0) --kk;
+        if (kk >= 0) {
+            ch.pos = c.base + (int64_t)(c.start + __ldg(g.T + kk));
+            ch.init = c.sum_left + (int64_t)kk * VS;
+        } else {
+            ch.pos = s0; ch.init = nullptr;
+        }
+    }
+    return ch;
+}
+
+// distance of one KL2 candidate from its two cached sides and running sums (one warp)
+__device__ __forceinline__ double gw_kl2_distance(const double* sideL, const double* sideR,
+                                                  const float* sumL, const float* sumR,
+                                                  double nL, double nR, int lane) {
+    double t1 = 0.0, t2 = 0.0;
+    const float fl = (float)nL, fr = (float)nR;
+    for (int j = lane; j < D39; j += 32) {
+        const float m0 = __fdiv_rn(__ldcg(sumL + j), fl), m1 = __fdiv_rn(__ldcg(sumR + j), fr);
+        const double delta = (double)__fsub_rn(m0, m1);
+        const double s0 = __ldcg(sideL + j), p0 = __ldcg(sideL + VS + j);
+        const double s1 = __ldcg(sideR + j), p1 = __ldcg(sideR + VS + j);
+        t1 += (s0 - s1) * (p1 - p0);
+        t2 += __dmul_rn(__dmul_rn(p0 + p1, delta), delta);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    }
+    return __dadd_rn(__dmul_rn(0.5, t1), __dmul_rn(0.5, t2));
 }
 
 template <bool KL2>
@@ -198,18 +400,38 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
     const int group = blockIdx.x / g.group_ctas;
     const int rank = blockIdx.x - group * g.group_ctas;      // CTA rank in its group
     const int gwarps = g.group_ctas * GW_WARPS;
-    const int gpairs = gwarps / 2;            // KL2: two warps (one per side) work on one candidate
     const int rterms = KL2 ? 1 : (g.metric == SPKDIAR_GLR ? 2 : 1);
     double* left = g.left + (int64_t)group * g.kmax;
     double* right = g.right + (int64_t)group * 2 * g.bmax * g.kmax * rterms;
     double* pooled = g.pooled + (int64_t)group * 2 * GW_BMAX;
     double* fine = g.fine + (int64_t)group * 2 * 3 * GW_JMAX;
+    // KL2 arrays of this group
+    double* kside_left = KL2 ? g.kside_left + (int64_t)group * g.kmax * KS : nullptr;
+    double* kside_right = KL2 ? g.kside_right + (int64_t)group * 2 * g.kcap * KS : nullptr;
+    double* kside_fine = KL2 ? g.kside_fine + (int64_t)group * 4 * GW_JMAX * KS : nullptr;
+    float* ksum_left = KL2 ? g.ksum_left + (int64_t)group * g.kmax * VS : nullptr;
+    float* ksum_right = KL2 ? g.ksum_right + (int64_t)group * 2 * g.kcap * VS : nullptr;
+    float* ksum_fine = KL2 ? g.ksum_fine + (int64_t)group * 4 * GW_JMAX * VS : nullptr;
+    GwKl2Warp* kwarps = reinterpret_cast<GwKl2Warp*>(scratch_base);
+    float* ring = reinterpret_cast<float*>(scratch_base + GW_WARPS * sizeof(GwKl2Warp));
+    uint64_t* ring_bar = reinterpret_cast<uint64_t*>(ring + GW_RING_STAGES * GW_STAGE_FLOATS);
+    long long* range = reinterpret_cast<long long*>(ring_bar + GW_RING_STAGES);
+    uint32_t ring_phase = 0;
+    if (KL2) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < GW_RING_STAGES; ++s) mbar_init(ring_bar + s, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
     unsigned long long* bar = g.bar + group;
     unsigned long long bar_target = 0;
     int wave = 0;               // parity source for the double-buffered term arrays
     int chain_pub = 0;          // parity of the published next-chain slot
 
     long long t_plan = 0, t_eval = 0, t_bar = 0, t_dec = 0, n_wave = 0, n_task = 0, t_e1 = 0, t_e2 = 0;
+    long long n_rows = 0, t_wait = 0;
+    long long t_chain = 0;      // KL2: cycles of warp 0 in the sum chains / of warp 1 in the sides
     int chain = group;
     while (chain < g.nchain) {
         // ---- chain state (identical in thread 0 of every CTA of the group) ----
@@ -226,6 +448,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
         double pend_e = 0.0, pend_maxi = 0.0, pend_maxd = 0.0;
         int pend_ncand = 0, pend_ninf = 0;
         bool want_fine = false;
+        int coarse_waves = 0;       // coarse waves since `start` last moved (thread 0)
+        if (threadIdx.x == 0) plan.chain_valid = 0;
 
         while (!done) {
             // ================= PLAN =================
@@ -238,7 +462,11 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     plan.mode = 0;
                     double e = end, w_ = ws, dw = dws;
                     int nW = 0;
-                    for (int w = 0; w < g.bmax; ++w) {
+                    // KL2 speculates less right after a change: the sum chains of a batch cost rows x offsets,
+                    // i.e. grow with the square of the depth, and most changes show within a few windows
+                    int depth = g.bmax;
+                    if (KL2 && g.bmax > 1) depth = coarse_waves == 0 ? 4 : (coarse_waves == 1 ? 8 : g.bmax);
+                    for (int w = 0; w < depth; ++w) {
                         plan.e[w] = e;
                         nW = w + 1;
                         // negative-branch growth, CD:273-284
@@ -281,50 +509,123 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     for (int w = 0; w < plan.nW; ++w) {
                         const int newl = plan.K[w] > kmaxw ? plan.K[w] - kmaxw : 0;
                         const int t = plan.K[w] * rterms + newl + ((!KL2 && g.metric == SPKDIAR_BIC) ? 1 : 0);
-                        if (w > 0 && tasks + t > (KL2 ? gpairs : gwarps)) break;
+                        if (w > 0 && tasks + t > gwarps) break;
                         tasks += t;
                         if (plan.K[w] > kmaxw) kmaxw = plan.K[w];
                         nW = w + 1;
                     }
                     plan.nW = nW;
                     plan.k0 = left_valid;
-                    plan.nL = KL2 ? 0 : (kmaxw - left_valid);
-                    int off = plan.nL + ((!KL2 && g.metric == SPKDIAR_BIC) ? nW : 0);
-                    for (int w = 0; w < nW; ++w) { plan.sec[w] = off; off += plan.K[w] * rterms; }
-                    plan.sec[nW] = off;
-                    plan.ntask = off;
+                    plan.nL = kmaxw - left_valid;
+                    plan.kmaxw = kmaxw;
+                    if (KL2) {
+                        // sec = candidate slots of window w; side tasks: nL lefts, then one right per slot
+                        int off = 0;
+                        for (int w = 0; w < nW; ++w) { plan.sec[w] = off; off += plan.K[w]; }
+                        plan.sec[nW] = off;
+                        plan.ntask = plan.nL + off;
+                    } else {
+                        int off = plan.nL + (g.metric == SPKDIAR_BIC ? nW : 0);
+                        for (int w = 0; w < nW; ++w) { plan.sec[w] = off; off += plan.K[w] * rterms; }
+                        plan.sec[nW] = off;
+                        plan.ntask = off;
+                    }
                 }
             } else if (threadIdx.x == 0) {
-                plan.ntask = plan.nJ * (KL2 ? 1 : (g.metric == SPKDIAR_GLR ? 3 : 2));
+                plan.ntask = plan.nJ * (KL2 ? 2 : (g.metric == SPKDIAR_GLR ? 3 : 2));
             }
             __syncthreads();
 
             // ================= EVALUATE =================
             const long long c1 = clock64();
             const int64_t s0 = base + (int64_t)start;
-            // A wave with fewer tasks than warps spreads over all SMs instead of filling the first
-            // CTAs.  BIC / GLR: task t -> CTA t % group_ctas.  KL2: every CTA takes a CONTIGUOUS
-            // chunk of the round (neighbouring candidates) for the cooperative mean pass.
-            for (int r0 = 0; r0 < plan.ntask; r0 += (KL2 ? gpairs : gwarps)) {
-                int id;
-                bool has;
-                if (KL2) {
-                    // two warps per candidate (left side / right side), gpairs candidates per round
-                    const int nround = plan.ntask - r0 < gpairs ? plan.ntask - r0 : gpairs;
-                    const int chunk = (nround + g.group_ctas - 1) / g.group_ctas;
-                    const int pi = warp >> 1;
-                    id = r0 + rank * chunk + pi;
-                    has = pi < chunk && rank * chunk + pi < nround;
-                } else {
-                    id = r0 + warp * g.group_ctas + rank;
-                    has = id < plan.ntask;
+            if (KL2) {
+                const long long k0c = clock64();
+                {
+                    // ---- sum chains: chain ct belongs to CTA ct % group_ctas, twelve per round ----
+                    GwChainCtx cc{&g, &plan, base, start, ksum_left, ksum_right, ksum_fine};
+                    const int nright = plan.mode == 0 ? plan.kmaxw : plan.nJ;
+                    const int nct = nright + ((plan.mode == 0 ? plan.nL : plan.nJ) > 0 ? 1 : 0);
+                    for (int c0 = rank; c0 < nct; c0 += g.group_ctas * GW_WARPS) {
+                        const int ct = c0 + warp * g.group_ctas;
+                        GwChain ch;
+                        ch.kind = 0; ch.a = 0; ch.w0 = 0; ch.nsnap = 0; ch.pos = 0; ch.init = nullptr;
+                        if (ct < nct) ch = gw_make_chain(cc, ct, nright, left_valid, s0);
+                        gw_sum_round(cc, ch, ct < nct && ch.nsnap > 0, range, ring, ring_bar, ring_phase, warp, lane,
+                                     n_rows, t_wait);
+                    }
+                    if (warp == 0) t_chain += clock64() - k0c;
                 }
-                int64_t mm = s0, ee = s0;
-                int term = 0;
-                double* dst = nullptr;
-                if (has) {
+                {
+                    // ---- sides: diag(S), diag(S^-1) of one window per task ----
+                    const long long k2c = clock64();
+                    GwKl2Warp& own = kwarps[warp];
+                    for (int id = warp * g.group_ctas + rank; id < plan.ntask; id += gwarps) {
+                        int64_t ra, rb;
+                        double* dst;
+                        if (plan.mode == 0) {
+                            if (id < plan.nL) {                                 // left side of a new offset
+                                const int k = plan.k0 + id;
+                                ra = s0; rb = base + (int64_t)(start + __ldg(g.T + k));
+                                dst = kside_left + (int64_t)k * KS;
+                            } else {                                            // right side of candidate slot t
+                                const int t = id - plan.nL;
+                                int w = 0;
+                                while (t >= plan.sec[w + 1]) ++w;
+                                const int k = t - plan.sec[w];
+                                ra = base + (int64_t)(start + __ldg(g.T + k));
+                                rb = base + (int64_t)plan.e[w];
+                                dst = kside_right + ((int64_t)parity * g.kcap + t) * KS;
+                            }
+                        } else {
+                            const int side = id >= plan.nJ ? 1 : 0, j = id - side * plan.nJ;
+                            const int64_t mm = base + (int64_t)(start + plan.fi[j]);
+                            ra = side ? mm : s0;
+                            rb = side ? base + (int64_t)plan.e[0] : mm;
+                            dst = kside_fine + ((int64_t)(parity * 2 + side) * GW_JMAX + j) * KS;
+                        }
+                        kl2_side_one(WinSrc(g.st, ra, rb, REC), own, dst, dst + VS, lane);
+                    }
+                    if (warp == 1) t_chain += clock64() - k2c;
+                }
+                const long long k1c = clock64();
+                gw_group_barrier(bar, bar_target, g.group_ctas);
+                t_e1 += k1c - k0c; t_e2 += clock64() - k1c;
+                // ---- distances: one warp per candidate ----
+                const int ncand = plan.mode == 0 ? plan.sec[plan.nW] : plan.nJ;
+                for (int t = warp * g.group_ctas + rank; t < ncand; t += gwarps) {
+                    const double *sl, *sr; const float *ml, *mr; int64_t mm, ee; double* dst;
                     if (plan.mode == 0) {
-                        const int npool = (!KL2 && g.metric == SPKDIAR_BIC) ? plan.nW : 0;
+                        int w = 0;
+                        while (t >= plan.sec[w + 1]) ++w;
+                        const int k = t - plan.sec[w];
+                        mm = base + (int64_t)(start + __ldg(g.T + k));
+                        ee = base + (int64_t)plan.e[w];
+                        sl = kside_left + (int64_t)k * KS;              ml = ksum_left + (int64_t)k * VS;
+                        sr = kside_right + ((int64_t)parity * g.kcap + t) * KS;
+                        mr = ksum_right + ((int64_t)parity * g.kcap + t) * VS;
+                        dst = right + ((int64_t)parity * g.bmax + w) * g.kmax + k;
+                    } else {
+                        mm = base + (int64_t)(start + plan.fi[t]);
+                        ee = base + (int64_t)plan.e[0];
+                        sl = kside_fine + ((int64_t)(parity * 2 + 0) * GW_JMAX + t) * KS;
+                        sr = kside_fine + ((int64_t)(parity * 2 + 1) * GW_JMAX + t) * KS;
+                        ml = ksum_fine + ((int64_t)(parity * 2 + 0) * GW_JMAX + t) * VS;
+                        mr = ksum_fine + ((int64_t)(parity * 2 + 1) * GW_JMAX + t) * VS;
+                        dst = fine + (int64_t)parity * 3 * GW_JMAX + t;
+                    }
+                    const double v = gw_kl2_distance(sl, sr, ml, mr, (double)(mm - s0), (double)(ee - mm), lane);
+                    if (lane == 0) *dst = v;
+                }
+            } else {
+                // A wave with fewer tasks than warps spreads over all SMs instead of filling the first
+                // CTAs: task t -> CTA t % group_ctas.
+                for (int id = warp * g.group_ctas + rank; id < plan.ntask; id += gwarps) {
+                    int64_t mm = s0, ee = s0;
+                    int term = 0;
+                    double* dst = nullptr;
+                    if (plan.mode == 0) {
+                        const int npool = g.metric == SPKDIAR_BIC ? plan.nW : 0;
                         if (id < plan.nL) {                         // left term of a new coarse offset
                             const int k = plan.k0 + id;
                             mm = base + (int64_t)(start + __ldg(g.T + k));
@@ -340,38 +641,17 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                             const int k = r / rterms, sub = r - k * rterms;
                             mm = base + (int64_t)(start + __ldg(g.T + k));
                             ee = base + (int64_t)plan.e[w];
-                            term = KL2 ? 3 : (sub == 0 ? 1 : 2);
+                            term = sub == 0 ? 1 : 2;
                             dst = right + (((int64_t)parity * g.bmax + w) * g.kmax + k) * rterms + sub;
                         }
                     } else {
-                        const int per = KL2 ? 1 : (g.metric == SPKDIAR_GLR ? 3 : 2);
+                        const int per = g.metric == SPKDIAR_GLR ? 3 : 2;
                         const int j = id / per, sub = id - j * per;
                         mm = base + (int64_t)(start + plan.fi[j]);
                         ee = base + (int64_t)plan.e[0];
-                        term = KL2 ? 3 : sub;
+                        term = sub;
                         dst = fine + ((int64_t)parity * 3 + sub) * GW_JMAX + j;
                     }
-                }
-                if (KL2) {
-                    Kl2Scratch* kall = reinterpret_cast<Kl2Scratch*>(scratch_base);
-                    Kl2Scratch& own = kall[warp];               // factorisation scratch of this warp
-                    Kl2Scratch& pair = kall[warp & ~1];         // results of the candidate (both sides)
-                    float* cring = reinterpret_cast<float*>(scratch_base + GW_WARPS * sizeof(Kl2Scratch));
-                    const int side = warp & 1;
-                    const long long ra = has ? (side ? mm : s0) : 0;
-                    const long long rb = has ? (side ? ee : mm) : 0;
-                    const long long k0 = clock64();
-                    if (has) kl2_side_one(WinSrc(g.st, ra, rb, REC), own, pair.dS[side], pair.dP[side], lane);
-                    const long long k1 = clock64();
-                    gw_cta_means(g.x, ra, rb, plan, cring, warp, lane, pair.mean[side]);   // ends with __syncthreads
-                    t_e1 += k1 - k0; t_e2 += clock64() - k1;
-                    if (has && side == 0) {
-                        double t1, t2;
-                        const double v = kl2_finish(pair, lane, &t1, &t2);
-                        if (lane == 0) *dst = v;
-                    }
-                    __syncthreads();                            // pair results consumed before the next round
-                } else if (has) {
                     WarpScratch& wsr = reinterpret_cast<WarpScratch*>(scratch_base)[warp];
                     const WinSrc X(g.st, s0, mm, REC);
                     const WinSrc Y(g.st, mm, ee, REC);
@@ -435,6 +715,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                             want_fine = true;
                             pend_e = plan.e[w]; pend_maxi = maxi; pend_maxd = maxd;
                             pend_ncand = plan.K[w]; pend_ninf = plan.ninf[w];
+                            plan.pend_bk = plan.bk[w];
                             if (!KL2 && g.metric == SPKDIAR_BIC) plan.pend_pl = __ldcg(pooled + parity * GW_BMAX + w);
                             end = plan.e[w];
                             break;
@@ -454,7 +735,16 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                         end = plan.e_after[w]; ws = plan.ws_after[w]; dws = plan.dws_after[w];
                         if (plan.last[w]) { done = true; break; }
                     }
-                    if (!KL2) left_valid = kmaxw;
+                    // every offset of the batch now has its left term / left side, and (KL2) a
+                    // running right sum that ends at the last window of the batch
+                    left_valid = plan.kmaxw;
+                    ++coarse_waves;
+                    if (KL2) {
+                        plan.chain_valid = plan.kmaxw;
+                        plan.chain_base = plan.sec[plan.nW - 1];
+                        plan.chain_parity = parity;
+                        plan.chain_row = base + (int64_t)plan.e[plan.nW - 1];
+                    }
                     plan.mode = done ? 2 : (want_fine ? 1 : 0);
                 }
             } else {
@@ -501,7 +791,9 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     }
                     ++seq;
                     want_fine = false;
+                    coarse_waves = 0;
                     left_valid = 0;                                     // CD:256
+                    plan.chain_valid = 0;
                     start += maxi;                                      // CD:263
                     if (start + g.winsize * 2 <= n) {                   // CD:264-268
                         end = start + g.winsize * 2;
@@ -535,18 +827,26 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
         chain = *((volatile int32_t*)(g.group_chain + group * 2 + chain_pub));
         chain_pub ^= 1;
     }
+    if (KL2 && g.dbg && lane == 0 && warp < 2) g.dbg[8 + 4 * blockIdx.x + warp] = t_chain;
+    if (KL2 && g.dbg && lane == 0 && warp == 0) { g.dbg[8 + 4 * blockIdx.x + 2] = n_rows; g.dbg[8 + 4 * blockIdx.x + 3] = t_wait; }
     if (g.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
         g.dbg[0] = t_plan; g.dbg[1] = t_eval; g.dbg[2] = t_bar; g.dbg[3] = t_dec; g.dbg[4] = n_wave; g.dbg[5] = n_task; g.dbg[6] = t_e1; g.dbg[7] = t_e2;
     }
 }
 
-inline cudaError_t gw_configure() {
+inline size_t gw_smem_bytes(bool kl2) {
     const size_t plan = (sizeof(GwPlan) + 15) & ~(size_t)15;
+    if (!kl2) return plan + GW_WARPS * sizeof(WarpScratch);
+    return plan + GW_WARPS * sizeof(GwKl2Warp) + sizeof(float) * GW_RING_STAGES * GW_STAGE_FLOATS
+           + sizeof(uint64_t) * GW_RING_STAGES + sizeof(long long) * 2 * GW_WARPS;
+}
+
+inline cudaError_t gw_configure() {
     cudaError_t e = cudaFuncSetAttribute(gw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(plan + GW_WARPS * sizeof(WarpScratch)));
+                                         (int)gw_smem_bytes(false));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(gw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(plan + GW_WARPS * sizeof(Kl2Scratch) + GW_CRING_BYTES));
+                                (int)gw_smem_bytes(true));
 }
 
 }  // namespace spk

@@ -193,8 +193,9 @@ __device__ __forceinline__ void seq_mean_f32(const float* __restrict__ x, const 
 
 // one side of a KL2 evaluation: diag(S) and diag(S^-1) of the window / cluster `gsrc`
 // into dS / dP (shared memory); `k` is the calling warp's own scratch.
-template <class Src>
-__device__ __forceinline__ void kl2_side_one(const Src& gsrc, Kl2Scratch& k, double* dS, double* dP, int lane) {
+// `k` is any scratch type with members w (LdlScratch), rec / Lsm (a union) and pinv.
+template <class Src, class Scr>
+__device__ __forceinline__ void kl2_side_one(const Src& gsrc, Scr& k, double* dS, double* dP, int lane) {
     const SmemSrc src{stage_record(gsrc, k.rec, lane)};
     __syncwarp();
     double hi[D39];
