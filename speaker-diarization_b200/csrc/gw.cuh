@@ -560,7 +560,9 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     // ---- sides: diag(S), diag(S^-1) of one window per task ----
                     const long long k2c = clock64();
                     GwKl2Warp& own = kwarps[warp];
-                    for (int id = warp * g.group_ctas + rank; id < plan.ntask; id += gwarps) {
+                    const int chunk = (plan.ntask + g.group_ctas - 1) / g.group_ctas;     // contiguous, see below
+                    const int id_end = (rank + 1) * chunk < plan.ntask ? (rank + 1) * chunk : plan.ntask;
+                    for (int id = rank * chunk + warp; id < id_end; id += GW_WARPS) {
                         int64_t ra, rb;
                         double* dst;
                         if (plan.mode == 0) {
@@ -619,8 +621,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                 }
             } else {
                 // A wave with fewer tasks than warps spreads over all SMs instead of filling the first
-                // CTAs: task t -> CTA t % group_ctas.
-                for (int id = warp * g.group_ctas + rank; id < plan.ntask; id += gwarps) {
+                // CTAs, in CONTIGUOUS chunks: neighbouring tasks are neighbouring offsets of one window,
+                // they share the records at the window end and (13 offsets at a time) the block prefix at
+                // the split, so most operand loads of a CTA's twelve warps meet in L1 instead of L2.
+                const int chunk = (plan.ntask + g.group_ctas - 1) / g.group_ctas;
+                const int id_end = (rank + 1) * chunk < plan.ntask ? (rank + 1) * chunk : plan.ntask;
+                for (int id = rank * chunk + warp; id < id_end; id += GW_WARPS) {
                     int64_t mm = s0, ee = s0;
                     int term = 0;
                     double* dst = nullptr;

@@ -1,25 +1,24 @@
-// layout.cuh - the "lane-paired" packed layout of a symmetric DxD matrix.
+// layout.cuh - (1) the layout of a sufficient-statistics record in HBM and
+// (2) which lane of a warp owns which entry of the DxD matrix it factorises.
 //
-// Every sufficient-statistics record in HBM (frame prefix records written by
-// the statistics kernels, per-cluster records of the clustering engine) is
-// RECORD = TRI + D + 1 doubles:
+// (1) Every record (frame prefix records written by the statistics kernels,
+// per-cluster records of the clustering engine) is RECORD = TRI + D + 1 doubles:
 //
-//   [0, TRI)        second moments  sum (x-c)_r (x-c)_k   (lower triangle, k <= r)
+//   [0, TRI)        second moments  sum (x-c)_r (x-c)_k,  k <= r, packed row-major:
+//                   entry (r, k) at r (r + 1) / 2 + k
 //   [TRI, TRI + D)  first moments   sum (x-c)_k
 //   [TRI + D]       frame count
 //
-// The triangle is NOT stored row-major.  It is stored in the order the
-// warp-level LDL^T factorisation wants to read it: lane l (l < NL) owns the
-// two rows  rh = D-1-l ("hi", D-l entries)  and  l ("lo", l+1 entries, only
-// when l < rh), so that every lane owns about the same number of entries, and
-// register slot hi[k] / lo[k] of consecutive lanes sit at consecutive
-// addresses:
-//
-//   lo[k] of lane l (k <= l < NLO)      at  off_lo(k) + (l - k)
-//   hi[k] of lane l (l <= min(NL-1, D-1-k))  at  off_hi(k) + l
-//
-// A warp therefore loads a whole record with coalesced 8-byte loads into
-// statically indexed registers - no shared-memory staging, no shuffles.
+// (2) The factorisation is a right-looking LDL^T whose trailing submatrix shrinks
+// with every step, so a lane that owns whole rows or columns idles more and more.
+// The lower triangle is therefore dealt out BLOCK-CYCLICALLY over the warp seen as
+// a 4 x 8 grid: lane (i, j), i = lane / 8, j = lane % 8, owns the entries (r, k)
+// with r % 4 == i and k % 8 == j.  At every step the live entries are spread evenly
+// over all 32 lanes (a lane updates at most 30 of its own entries in the first step,
+// about n_live / 32 later), where a row-per-lane layout needs 58 updates per lane on
+// 20 lanes.  A lane keeps its entries in statically indexed registers: local row
+// ri = r / 4 (0..9), local column kj = k / 8 (0..4); only the slots with ri >= 2 kj
+// can lie on or below the diagonal, 30 slots in all.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -29,48 +28,29 @@ namespace spk {
 
 template <int D>
 struct Layout {
-    static constexpr int NL  = (D + 1) / 2;        // lanes that own rows
-    static constexpr int NLO = D / 2;              // lanes that also own a "lo" row
     static constexpr int TRI = D * (D + 1) / 2;
     static constexpr int REC = TRI + D + 1;        // doubles per record
     static constexpr int VEC = TRI;                // offset of first moments
     static constexpr int CNT = TRI + D;            // offset of frame count
-
-    __host__ __device__ static constexpr int off_lo(int k) {
-        return k * NLO - (k * (k - 1)) / 2;
-    }
-    static constexpr int TLO = NLO * (NLO + 1) / 2;
-    __host__ __device__ static constexpr int cnt_hi(int k) {
-        return (D - k) < NL ? (D - k) : NL;
-    }
-    __host__ __device__ static constexpr int off_hi(int k) {
-        int o = TLO;
-        for (int j = 0; j < k; ++j) o += cnt_hi(j);
-        return o;
-    }
-    // closed form of off_hi for run-time k
-    __host__ __device__ static constexpr int off_hi_rt(int k) {
-        constexpr int K0 = D - NL + 1;             // columns 0..K0-1 are held by all NL lanes
-        return k <= K0 ? TLO + k * NL
-                       : TLO + K0 * NL + (k - K0) * D - ((K0 + k - 1) * (k - K0)) / 2;
-    }
-    __host__ __device__ static constexpr bool off_hi_rt_ok() {
-        for (int k = 0; k <= D; ++k) if (off_hi_rt(k) != off_hi(k)) return false;
-        return true;
-    }
-    // position of the diagonal element (j, j), run-time j
-    __host__ __device__ static constexpr int pos_diag(int j) {
-        return (j < D - 1 - j) ? off_lo(j) : off_hi_rt(j) + (D - 1 - j);
-    }
-    // position of element (r, c), c <= r
-    __host__ __device__ static constexpr int pos(int r, int c) {
-        return (r < D - 1 - r) ? off_lo(c) + (r - c)          // a "lo" row of lane r
-                               : off_hi(c) + (D - 1 - r);     // a "hi" row of lane D-1-r
-    }
+    __host__ __device__ static constexpr int pos(int r, int c) { return (r * (r + 1)) / 2 + c; }   // c <= r
+    __host__ __device__ static constexpr int pos_diag(int j) { return (j * (j + 3)) / 2; }
 };
 
-static_assert(Layout<39>::off_hi(39) == Layout<39>::TRI, "layout must tile the triangle");
+template <int D>
+struct Grid {
+    static constexpr int PR = 4, PC = 8;                       // lane grid
+    static constexpr int NRI = (D + PR - 1) / PR;              // local rows    (10 for D = 39)
+    static constexpr int NKJ = (D + PC - 1) / PC;              // local columns ( 5 for D = 39)
+    static constexpr int RPK = PC / PR;                        // local rows per local column step (2)
+    // slots of local column kj: local rows RPK * kj .. NRI - 1
+    __host__ __device__ static constexpr int off(int kj) { return kj * NRI - RPK * (kj * (kj - 1)) / 2; }
+    static constexpr int NSLOT = off(NKJ);                     // 30 for D = 39
+    __host__ __device__ static constexpr int slot(int kj, int ri) { return off(kj) + ri - RPK * kj; }
+    __host__ __device__ static constexpr int ri_first(int kj) { return RPK * kj; }
+};
+
 static_assert(Layout<39>::REC == 820, "record size");
-static_assert(Layout<39>::off_hi_rt_ok(), "closed form of off_hi");
+static_assert(Grid<39>::NSLOT == 30, "slots per lane");
+static_assert(Grid<39>::NRI * Grid<39>::PR >= 39 && Grid<39>::NKJ * Grid<39>::PC >= 39, "grid covers the matrix");
 
 }  // namespace spk

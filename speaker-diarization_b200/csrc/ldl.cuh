@@ -6,13 +6,11 @@
 // sufficient-statistics records, factorised as L diag(p) L^T without square
 // roots, and  ln|S| = sum ln p_c - D ln(n-1).
 //
-// Register layout: see layout.cuh.  Lane l holds row rh = D-1-l in hi[0..D-1]
-// (entries k <= rh are meaningful) and row l in lo[0..NLO-1] (k <= l, only when
-// l < NLO).  The factorisation is right-looking: at step c every lane
-// publishes its entry of column c to a 2x(D+1)-double shared-memory strip, one
-// __syncwarp later all lanes read the pivot and the column back as broadcast
-// loads and apply the rank-1 update to their own rows from registers.  Slots a
-// lane does not own carry garbage that is never published.
+// Register layout: see layout.cuh (block-cyclic 4 x 8 lane grid, 30 slots per
+// lane).  The factorisation is right-looking: at step c the owners of column c
+// publish it to a 2x40-double shared-memory strip, one __syncwarp later all lanes
+// read the pivot and the entries they need back and apply the rank-1 update to
+// their own slots from registers.
 #pragma once
 
 #include "layout.cuh"
@@ -83,26 +81,37 @@ struct SumSrc {
 
 // ---- staging -------------------------------------------------------------------
 // Stage one statistics record into shared memory.  This is the MEMORY phase of a
-// task: lane-strided, fully coalesced, 8 independent element loads in flight per
-// lane and almost no live registers - whereas loading straight into the 58-double
+// task: lane-strided, fully coalesced, B independent element loads in flight per
+// lane and almost no other live registers - whereas loading straight into the
 // register tile of the factorisation left one load in flight at a time (ncu: 62 % of
 // the stall samples on the consuming DADDs, profiles/r01_win_terms_before.txt).
-template <class Src>
-__device__ __forceinline__ const double* stage_record(const Src& src, double* buf, int lane) {
+template <int B, class Src>
+__device__ __forceinline__ void stage_batches(const Src& src, double* buf, int lane) {
 #pragma unroll 1
-    for (int q0 = 0; q0 < REC39; q0 += 32 * 8) {
-        double t[8];
+    for (int q0 = 0; q0 < REC39; q0 += 32 * B) {
+        double t[B];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < B; ++u) {
             const int q = q0 + 32 * u + lane;
             t[u] = q < REC39 ? src(q) : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < B; ++u) {
             const int q = q0 + 32 * u + lane;
             if (q < REC39) buf[q] = t[u];
         }
     }
+}
+template <class Src>
+__device__ __forceinline__ const double* stage_record(const Src& src, double* buf, int lane) {
+    stage_batches<13>(src, buf, lane);                // 26 elements per lane: two round trips
+    return buf;
+}
+// a window of the two-level statistics: two loads per element inside one block, four
+// (two of them 16 bytes wide) across blocks
+__device__ __forceinline__ const double* stage_record(const WinSrc& src, double* buf, int lane) {
+    if (src.cross) stage_batches<9>(src, buf, lane);
+    else stage_batches<13>(src, buf, lane);
     return buf;
 }
 // a record that already sits in shared memory is used in place
@@ -118,50 +127,51 @@ __device__ __forceinline__ const double* stage_record(const SmemSrc& src, double
 //   FORM_POOL  M = (Qx+Qy) - (sx+sy)(sx+sy)^T / (nx+ny)      (BIC pooled term)
 //   FORM_MIX   M = wx (Qx - sx sx^T/nx) + wy (Qy - sy sy^T/ny)   (GLR, CD:114-115)
 //
-// Returns the frame count the matrix stands for (nx, ny, nx+ny; 0 for MIX).
+// Lane (i, j) = (lane / 8, lane % 8) fills its slots (kj, ri) <-> entry (i + 4 ri, j + 8 kj),
+// see layout.cuh.  Returns the frame count the matrix stands for (nx, ny, nx+ny; 0 for MIX).
 enum { FORM_X = 0, FORM_Y = 1, FORM_POOL = 2, FORM_MIX = 3 };
 
 template <int D, class SrcX, class SrcY>
-__device__ __forceinline__ double form_matrix(double (&hi)[D], double (&lo)[Layout<D>::NLO > 0 ? Layout<D>::NLO : 1],
+__device__ __forceinline__ double form_matrix(double (&a)[Grid<D>::NSLOT],
                                               int kind, const SrcX& x, const SrcY& y, double wx, double wy,
                                               LdlScratch& w, int lane) {
     using L = Layout<D>;
+    using G = Grid<D>;
     const bool ux = kind != FORM_Y, uy = kind != FORM_X;
     const bool two = kind == FORM_MIX;                 // second rank-1 correction
     const double nx = ux ? x(L::CNT) : 0.0, ny = uy ? y(L::CNT) : 0.0;
-    // v1 / v2: the first-moment vectors of the rank-1 corrections
-    for (int j = lane; j < D; j += 32) {
-        const double sx = ux ? x(L::VEC + j) : 0.0, sy = uy ? y(L::VEC + j) : 0.0;
-        w.s0[j] = two ? sx : sx + sy;
-        w.s1[j] = two ? sy : 0.0;
+    // s0 / s1: the first-moment vectors of the rank-1 corrections
+    for (int t = lane; t < VS; t += 32) {
+        const double sx = (ux && t < D) ? x(L::VEC + t) : 0.0, sy = (uy && t < D) ? y(L::VEC + t) : 0.0;
+        w.s0[t] = two ? sx : sx + sy;
+        w.s1[t] = two ? sy : 0.0;
     }
     __syncwarp();
     double ax = ux ? 1.0 : 0.0, ay = uy ? 1.0 : 0.0, c1, c2 = 0.0;
     if (two) { ax = wx; ay = wy; c1 = wx / nx; c2 = wy / ny; }
     else c1 = 1.0 / (nx + ny);
-    const int rh = (D - 1 - lane) >= 0 ? (D - 1 - lane) : 0;
-    const int rl = lane < D ? lane : 0;
-    const double u1h = w.s0[rh] * c1, u2h = w.s1[rh] * c2;
-    const double u1l = w.s0[rl] * c1, u2l = w.s1[rl] * c2;
+    const int i = lane >> 3, j = lane & 7;
+    double u1[G::NRI], u2[G::NRI];
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
-        const int q = L::off_hi(k) + lane;
-        double m = 0.0;
-        if (ux) m = ax * x(q);
-        if (uy) m = fma(ay, y(q), m);
-        m = fma(-u1h, w.s0[k], m);
-        if (two) m = fma(-u2h, w.s1[k], m);
-        hi[k] = m;
+    for (int ri = 0; ri < G::NRI; ++ri) {
+        u1[ri] = w.s0[i + G::PR * ri] * c1;            // index <= 39 < VS
+        u2[ri] = w.s1[i + G::PR * ri] * c2;
     }
 #pragma unroll
-    for (int k = 0; k < L::NLO; ++k) {
-        const int q = L::off_lo(k) - k + lane;
-        double m = 0.0;
-        if (ux) m = ax * x(q);
-        if (uy) m = fma(ay, y(q), m);
-        m = fma(-u1l, w.s0[k], m);
-        if (two) m = fma(-u2l, w.s1[k], m);
-        lo[k] = m;
+    for (int kj = 0; kj < G::NKJ; ++kj) {
+        const int k = j + G::PC * kj;
+        const double sk0 = w.s0[k], sk1 = w.s1[k];
+#pragma unroll
+        for (int ri = G::ri_first(kj); ri < G::NRI; ++ri) {
+            const int r = i + G::PR * ri;
+            const int q = (r < D && k <= r) ? L::pos(r, k) : 0;       // slots above the diagonal / outside: any value
+            double m = 0.0;
+            if (ux) m = ax * x(q);
+            if (uy) m = fma(ay, y(q), m);
+            m = fma(-u1[ri], sk0, m);
+            if (two) m = fma(-u2[ri], sk1, m);
+            a[G::slot(kj, ri)] = m;
+        }
     }
     __syncwarp();
     return two ? 0.0 : nx + ny;
@@ -173,52 +183,122 @@ __device__ __forceinline__ double form_matrix(double (&hi)[D], double (&lo)[Layo
 // r(r-1)/2) in Lsm and the reciprocal pivots in pinv (both shared memory).
 // One elimination step, column C known at compile time (template recursion: nvcc does
 // not fully unroll a 39-trip loop with this much body, and a rolled loop would index
-// the register arrays dynamically, i.e. push them to local memory).
+// the register array dynamically, i.e. push it to local memory):
+//   the owners of column C publish it to the shared-memory strip; every lane reads the
+//   pivot, the column entries of its own rows (scaled by 1/pivot) and of its own columns,
+//   and applies the rank-1 update to its live slots.  Slots that are finished or lie
+//   outside the triangle receive garbage that is never published.
+// predicated shared-memory store without a branch: the elimination steps stay one
+// straight-line block, so the instruction scheduler can overlap the tail of one step
+// (updates nobody waits for) with the latency chain of the next (strip round trip,
+// reciprocal, first multiply)
+__device__ __forceinline__ void st_shared_if(bool p, double* addr, double v) {
+    asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %0, 0;\n@q st.shared.f64 [%1], %2;\n}\n"
+                 ::"r"((int)p), "r"((unsigned)__cvta_generic_to_shared(addr)), "d"(v) : "memory");
+}
+// 1 / a to within an ulp without the slow-path branch of __drcp_rn: hardware seed y
+// (20 bits), e = 1 - a y, 1 / a = y (1 + e + e^2 + O(e^3)).  a <= 0, inf, NaN or
+// subnormal give inf / NaN, which the caller reports as a failed factorisation.
+__device__ __forceinline__ double fast_rcp(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double e = fma(-a, y, 1.0);
+    const double f = fma(e, e, e);
+    return fma(y, f, y);
+}
+
+// One elimination step.  On entry the lane already holds what it needs of column C
+// (read from the strip by the previous step): the pivot, the entries vr[] of its own
+// rows and vk[] of its own columns, and q = 1 / pivot is on its way.  The step
+// (1) updates column C + 1 and publishes it, (2) reads its part of column C + 1 back
+// and starts the next reciprocal, (3) applies the rest of the rank-1 update.
+// (Measured on B200, one warp alone: 195 cycles per step, of which about 105 are the
+// dependent chain strip round trip -> reciprocal -> multiply -> FMA and the rest is
+// fp64 issue time that the static schedule does not overlap with the chain; a variant
+// that takes the next pivot by warp shuffle to shorten the chain was slower.)
 template <int D, bool STORE, int C>
 struct LdlStep {
-    using L = Layout<D>;
-    static __device__ __forceinline__ void run(double (&hi)[D], double (&lo)[L::NLO > 0 ? L::NLO : 1],
-                                               LdlScratch& w, int lane, double& p0, double& p1, bool& bad,
-                                               double* Lsm, double* pinv) {
-        const int rh = D - 1 - lane;           // my hi row (valid when lane < NL)
-        double* v = w.v[C & 1];
-        if (lane < L::NL && rh >= C) v[rh] = hi[C];
-        if (C < L::NLO) { if (lane < L::NLO && lane >= C) v[lane] = lo[C < L::NLO ? C : 0]; }
-        __syncwarp();
-        const double piv = v[C];
+    using G = Grid<D>;
+    static __device__ __forceinline__ void run(double (&a)[G::NSLOT], LdlScratch& w, int lane, int i, int j,
+                                               const double (&vr)[G::NRI], const double (&vk)[G::NKJ],
+                                               double piv, double q,
+                                               double& p0, double& p1, bool& bad, double* Lsm, double* pinv) {
+        constexpr int ri_a = (C + 1) / G::PR;          // first local row that can hold a row > C
+        constexpr int kj_a = (C + 1) / G::PC;          // first local column that can hold a column > C
+        constexpr int kn = (C + 1) / G::PC, jn = (C + 1) % G::PC;     // local column / owner lanes of column C + 1
+        double* vn = w.v[(C + 1) & 1];
         bad |= !(piv > 0.0);
         if ((C & 31) == lane) { if (C < 32) p0 = piv; else p1 = piv; }
-        const double r = __drcp_rn(piv);
-        const double lh = hi[C] * r;
+        double lr[G::NRI];
+#pragma unroll
+        for (int ri = ri_a; ri < G::NRI; ++ri) lr[ri] = vr[ri] * q;
+        double nvr[G::NRI], nvk[G::NKJ], npiv = 1.0, nq = 1.0;
+        if (C + 1 < D) {
+            // (1) column C + 1 first: update it and hand it over at once
+#pragma unroll
+            for (int ri = (ri_a > G::ri_first(kn) ? ri_a : G::ri_first(kn)); ri < G::NRI; ++ri) {
+                const int r = i + G::PR * ri;
+                const double m = fma(-lr[ri], vk[kn], a[G::slot(kn, ri)]);
+                a[G::slot(kn, ri)] = m;
+                st_shared_if(j == jn && r > C && r < D, vn + r, m);
+            }
+            __syncwarp();
+            // (2) what the next step needs of column C + 1
+            constexpr int ri_n = (C + 2) / G::PR, kj_n = (C + 2) / G::PC;
+            npiv = vn[C + 1];
+#pragma unroll
+            for (int ri = ri_n; ri < G::NRI; ++ri) nvr[ri] = vn[i + G::PR * ri];
+#pragma unroll
+            for (int kj = kj_n; kj < G::NKJ; ++kj) nvk[kj] = vn[j + G::PC * kj];
+            nq = fast_rcp(npiv);
+            // (3) the rest of the update of step C
+#pragma unroll
+            for (int kj = kj_a; kj < G::NKJ; ++kj) {
+                if (kj == kn) continue;
+#pragma unroll
+                for (int ri = (ri_a > G::ri_first(kj) ? ri_a : G::ri_first(kj)); ri < G::NRI; ++ri)
+                    a[G::slot(kj, ri)] = fma(-lr[ri], vk[kj], a[G::slot(kj, ri)]);
+            }
+        }
         if (STORE) {
-            if (lane < L::NL && rh > C) Lsm[(rh * (rh - 1)) / 2 + C] = lh;
-            if (lane == 0) pinv[C] = r;
-        }
+            constexpr int jC = C % G::PC;
 #pragma unroll
-        for (int c2 = C + 1; c2 < D; ++c2) hi[c2] = fma(-lh, v[c2], hi[c2]);
-        if (C < L::NLO) {
-            const double ll = lo[C < L::NLO ? C : 0] * r;
-            if (STORE) { if (lane < L::NLO && lane > C) Lsm[(lane * (lane - 1)) / 2 + C] = ll; }
-#pragma unroll
-            for (int c2 = C + 1; c2 < L::NLO; ++c2) lo[c2] = fma(-ll, v[c2], lo[c2]);
+            for (int ri = ri_a; ri < G::NRI; ++ri) {
+                const int r = i + G::PR * ri;
+                st_shared_if(j == jC && r > C && r < D, Lsm + (r * (r - 1)) / 2 + C, lr[ri]);
+            }
+            st_shared_if(lane == 0, pinv + C, q);
         }
-        LdlStep<D, STORE, C + 1>::run(hi, lo, w, lane, p0, p1, bad, Lsm, pinv);
+        LdlStep<D, STORE, C + 1>::run(a, w, lane, i, j, nvr, nvk, npiv, nq, p0, p1, bad, Lsm, pinv);
     }
 };
 template <int D, bool STORE>
 struct LdlStep<D, STORE, D> {
-    using L = Layout<D>;
-    static __device__ __forceinline__ void run(double (&)[D], double (&)[L::NLO > 0 ? L::NLO : 1], LdlScratch&, int,
+    using G = Grid<D>;
+    static __device__ __forceinline__ void run(double (&)[G::NSLOT], LdlScratch&, int, int, int,
+                                               const double (&)[G::NRI], const double (&)[G::NKJ], double, double,
                                                double&, double&, bool&, double*, double*) {}
 };
 
 template <int D, bool STORE>
-__device__ __forceinline__ double ldl_logdet(double (&hi)[D], double (&lo)[Layout<D>::NLO > 0 ? Layout<D>::NLO : 1],
-                                             LdlScratch& w, int lane,
+__device__ __forceinline__ double ldl_logdet(double (&a)[Grid<D>::NSLOT], LdlScratch& w, int lane,
                                              double* Lsm = nullptr, double* pinv = nullptr) {
+    using G = Grid<D>;
     double p0 = 1.0, p1 = 1.0;             // pivots c == lane and c == lane + 32
     bool bad = false;
-    LdlStep<D, STORE, 0>::run(hi, lo, w, lane, p0, p1, bad, Lsm, pinv);
+    const int i = lane >> 3, j = lane & 7;
+    __syncwarp();                          // the strips may still be read by a slower lane of the previous task
+#pragma unroll
+    for (int ri = 0; ri < G::NRI; ++ri)    // prologue: publish column 0 and read it back
+        st_shared_if(j == 0 && i + G::PR * ri < D, w.v[0] + i + G::PR * ri, a[G::slot(0, ri)]);
+    __syncwarp();
+    double vr[G::NRI], vk[G::NKJ];
+    const double piv = w.v[0][0];
+#pragma unroll
+    for (int ri = 0; ri < G::NRI; ++ri) vr[ri] = w.v[0][i + G::PR * ri];
+#pragma unroll
+    for (int kj = 0; kj < G::NKJ; ++kj) vk[kj] = w.v[0][j + G::PC * kj];
+    LdlStep<D, STORE, 0>::run(a, w, lane, i, j, vr, vk, piv, fast_rcp(piv), p0, p1, bad, Lsm, pinv);
     double s = log(p0);
     if (D > 32) s += log(p1);
 #pragma unroll
@@ -242,9 +322,11 @@ __device__ __forceinline__ double finish_logdet(double ln_m, double n, int d) {
 // pair (j = l, rows l..D-1) and (j = D-1-l, rows D-1-l..D-1).
 //   diag(M^-1)_j = sum_{r >= j} X_rj^2 / p_r
 // Returns the value for column `lane` in ga and for column D-1-lane in gb.
+template <int D>
+struct InvCols { static constexpr int NL = (D + 1) / 2; };     // lanes that own column pairs of L^-1
 template <int D, int R>
 struct InvRow {
-    using L = Layout<D>;
+    using L = InvCols<D>;
     static constexpr int HB = D - L::NL;
     static __device__ __forceinline__ void run(const double* Lsm, int lane, double (&xa)[D], double (&xb)[L::NL]) {
         const double* row = Lsm + (R * (R - 1)) / 2;
@@ -268,14 +350,14 @@ struct InvRow {
 };
 template <int D>
 struct InvRow<D, D> {
-    using L = Layout<D>;
+    using L = InvCols<D>;
     static __device__ __forceinline__ void run(const double*, int, double (&)[D], double (&)[L::NL]) {}
 };
 
 template <int D>
 __device__ __forceinline__ void inv_diag(const double* Lsm, const double* pinv, int lane,
                                          double& ga, double& gb) {
-    using L = Layout<D>;
+    using L = InvCols<D>;
     constexpr int HB = D - L::NL;          // first row of the short columns (19 for D = 39)
     double xa[D];                          // column `lane`, indexed by row
     double xb[L::NL];                      // column D-1-lane, rows HB..D-1 -> index r - HB

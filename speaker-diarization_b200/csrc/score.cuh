@@ -77,13 +77,12 @@ __device__ __forceinline__ double logdet_term(int term, int metric, const SrcX& 
     if (kind != FORM_X) ry = stage_record(Y, w.rec[1], lane);
     __syncwarp();
     // compute phase
-    double hi[D39];
-    double lo[L39::NLO];
+    double a[Grid<D39>::NSLOT];
     const SmemSrc sx{rx}, sy{ry};
     double wx = 1.0, wy = 1.0;
     if (kind == FORM_MIX) glr_weights(sx(L39::CNT), sy(L39::CNT), wx, wy);
-    const double n = form_matrix<D39>(hi, lo, kind, sx, sy, wx, wy, w, lane);
-    const double lm = ldl_logdet<D39, false>(hi, lo, w, lane);
+    const double n = form_matrix<D39>(a, kind, sx, sy, wx, wy, w, lane);
+    const double lm = ldl_logdet<D39, false>(a, w, lane);
     if (kind == FORM_MIX) return range_map(lm);
     return finish_logdet(lm, n, D39);
 }
@@ -198,20 +197,19 @@ template <class Src, class Scr>
 __device__ __forceinline__ void kl2_side_one(const Src& gsrc, Scr& k, double* dS, double* dP, int lane) {
     const SmemSrc src{stage_record(gsrc, k.rec, lane)};
     __syncwarp();
-    double hi[D39];
-    double lo[L39::NLO];
-    const double n = form_matrix<D39>(hi, lo, FORM_X, src, src, 1.0, 1.0, k.w, lane);
+    double a[Grid<D39>::NSLOT];
+    const double n = form_matrix<D39>(a, FORM_X, src, src, 1.0, 1.0, k.w, lane);
     const double rn1 = 1.0 / (n - 1.0);
     for (int j = lane; j < D39; j += 32) {
         const double s = k.w.s0[j];
         dS[j] = (src(L39::pos_diag(j)) - s * s / n) * rn1;
     }
     __syncwarp();                       // the record buffer becomes the factor store
-    const double lm = ldl_logdet<D39, true>(hi, lo, k.w, lane, k.Lsm, k.pinv);
+    const double lm = ldl_logdet<D39, true>(a, k.w, lane, k.Lsm, k.pinv);
     double ga, gb;
     inv_diag<D39>(k.Lsm, k.pinv, lane, ga, gb);
     const bool bad = !(lm == lm);
-    if (lane < L39::NL) {
+    if (lane < InvCols<D39>::NL) {
         dP[lane] = bad ? d_nan() : ga * (n - 1.0);
         dP[D39 - 1 - lane] = bad ? d_nan() : gb * (n - 1.0);
     }
