@@ -34,7 +34,8 @@
 // so the kernel keeps one running sum per candidate offset ("sum chain") alive in
 // HBM across windows and waves, and a wave only adds the new rows.  The rows are
 // streamed through a shared-memory ring filled by bulk asynchronous copies (TMA),
-// twelve chains (one per warp) sharing one stream per CTA.  Left
+// four chains (one per chain warp) sharing one stream per CTA while the other warps
+// factorise.  Left
 // sides are cached per offset exactly like the left BIC term.  A KL2 wave has two
 // steps separated by a group barrier: sides + sums, then the distances.
 #pragma once
@@ -57,6 +58,8 @@ constexpr int KS = 2 * VS;              // doubles per cached KL2 side: diag(S)[
 constexpr int GW_RING_ROWS = 64;        // frame rows per ring stage (a multiple of 4: 16-byte spans)
 constexpr int GW_RING_STAGES = 6;
 constexpr int GW_STAGE_FLOATS = GW_RING_ROWS * D39;
+constexpr int GW_CHAIN_WARPS = 4;       // KL2: the last four warps (one per sub-partition) run the sum chains
+constexpr int GW_CHAIN_WARP0 = GW_WARPS - GW_CHAIN_WARPS;
 
 struct GwDev {                 // kernel parameters
     Stats st;                  // two-level frame statistics
@@ -64,6 +67,7 @@ struct GwDev {                 // kernel parameters
     int64_t nrows;             // frames in the recording
     const double* T;           // candidate offset table, kmax entries
     int64_t kmax;
+    int32_t t_exact;           // T[k] == minfeas + k * istep bit for bit: no table loads
     const int64_t* seg_a;      // chains
     const int64_t* seg_b;
     int32_t nchain;
@@ -72,6 +76,7 @@ struct GwDev {                 // kernel parameters
     int32_t bmax;              // speculation depth actually used (<= GW_BMAX)
     double rate, winsize, winstep, deltaws, threshold, lambda, minfeas, istep;
     int32_t metric;
+    int32_t kl2_depth[3];      // KL2 speculation depth of the 1st, 2nd and later coarse waves after a change
     // workspaces, per group
     double* left;              // [ngroups][kmax]
     double* right;             // [ngroups][2 parity][bmax][kmax][rterms]
@@ -91,7 +96,9 @@ struct GwDev {                 // kernel parameters
     // output
     spkdiar_gw_window* win;
     int64_t win_cap;
-    unsigned long long* nwin;  // records produced (may exceed win_cap -> E_CAPACITY)
+    unsigned long long* nwin;  // output slots claimed (blocks of GW_SLOT_BLOCK; unused slots keep chain = -1)
+    unsigned long long* nrec;  // records produced
+    long long* trace;          // optional per-wave trace of CTA 0 (KL2)
     unsigned long long* dbg;   // optional phase cycle counters of CTA 0: plan, eval, barrier, decide, waves, tasks
 };
 
@@ -106,6 +113,10 @@ struct GwPlan {                // shared memory, written by thread 0
     int rterms;
     int kmaxw;                 // largest candidate count of the batch
     int pend_bk;               // coarse maximum of the window waiting for its fine tune
+    int left_valid;            // offsets k < left_valid have a cached left term / left side
+    int side_next;             // KL2: next unclaimed side task of this CTA's chunk
+    double start;              // window start of the chain (fp64, chain-relative)
+    double pl[GW_BMAX];        // BIC: pooled term of window w
     // KL2 sum chains that survive from the previous coarse wave of the same `start`
     int chain_valid;           // offsets k < chain_valid have a running right sum ...
     int chain_base;            // ... in slot chain_base + k of parity chain_parity ...
@@ -151,15 +162,8 @@ __device__ __forceinline__ void gw_group_barrier(unsigned long long* ctr, unsign
     }
 }
 
-// count of k with T[k] < lim (T strictly increasing), from an arithmetic guess
-__device__ __forceinline__ int gw_count_below(const double* __restrict__ T, int64_t kmax, double lim,
-                                              double minfeas, double istep) {
-    double g = (lim - minfeas) / istep;
-    int64_t k = g > 0.0 ? (int64_t)g : 0;
-    if (k > kmax) k = kmax;
-    while (k < kmax && __ldg(T + k) < lim) ++k;
-    while (k > 0 && !(__ldg(T + k - 1) < lim)) --k;
-    return (int)k;
+__device__ __forceinline__ double gw_Tp(const GwDev* g, int64_t k) {      // see gw_T below
+    return g->t_exact ? __dadd_rn(g->minfeas, __dmul_rn((double)k, g->istep)) : __ldg(g->T + k);
 }
 
 // ---- KL2: sum chains ---------------------------------------------------------------------
@@ -170,8 +174,8 @@ __device__ __forceinline__ int gw_count_below(const double* __restrict__ T, int6
 //   kind 1  coarse left chain: continues the running sum of [start, .) through the new offsets
 //   kind 2  fine right chain of fine candidate j = a: rows [m_j, end)
 //   kind 3  fine left chain: from the nearest cached coarse offset through the fine offsets
-// Chain ct of a wave belongs to CTA ct % group_ctas; a CTA runs its chains twelve at a time,
-// one per warp, over ONE stream of rows: thread 0 feeds a shared-memory ring with bulk copies
+// Chain ct of a wave belongs to CTA ct % group_ctas; a CTA runs its chains four at a time,
+// one per chain warp, over ONE stream of rows: one thread feeds a shared-memory ring with bulk copies
 // (TMA) of GW_RING_ROWS rows, every warp adds the rows of its own range from the ring.
 struct GwChain { int kind, a, w0, nsnap; long long pos; const float* init; };
 
@@ -184,7 +188,7 @@ struct GwChainCtx {
 __device__ __forceinline__ long long gw_snap_row(const GwChainCtx& c, const GwChain& ch, int i) {
     switch (ch.kind) {
         case 0:  return c.base + (int64_t)c.plan->e[ch.w0 + i];
-        case 1:  return c.base + (int64_t)(c.start + __ldg(c.g->T + c.plan->k0 + i));
+        case 1:  return c.base + (int64_t)(c.start + gw_Tp(c.g, c.plan->k0 + i));
         case 2:  return c.base + (int64_t)c.plan->e[0];
         default: return c.base + (int64_t)(c.start + c.plan->fi[i]);
     }
@@ -199,59 +203,71 @@ __device__ __forceinline__ float* gw_snap_dst(const GwChainCtx& c, const GwChain
     }
 }
 
-// One round of the sum pass: every warp of the CTA runs (at most) one chain.  `range` is
-// a shared-memory scratch of 2 * GW_WARPS long longs, `phase` the mbarrier phase bit of
-// every ring stage (identical in all threads, lives as long as the kernel).
+// One round of the sum pass: each of the GW_CHAIN_WARPS chain warps of the CTA runs (at
+// most) one chain; they synchronise among themselves on named barrier 1, the other warps
+// of the CTA factorise meanwhile.  `range` is a shared-memory scratch of 2 * GW_CHAIN_WARPS
+// long longs, `phase` the mbarrier phase bit of every ring stage (identical in all chain
+// threads, lives as long as the kernel).  cw = index of the calling chain warp.
+__device__ __forceinline__ void gw_chain_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(GW_CHAIN_WARPS * 32) : "memory");
+}
 __device__ __forceinline__ void gw_sum_round(const GwChainCtx& c, const GwChain& ch, bool active,
                                              long long* range, float* ring, uint64_t* bars, uint32_t& phase,
-                                             int warp, int lane, long long& dbg_rows, long long& dbg_wait) {
+                                             int cw, int lane, long long& dbg_rows, long long& dbg_wait) {
     const float* __restrict__ x = c.g->x;
     const bool second = lane + 32 < D39;
     float s0 = 0.f, s1 = 0.f;
     int si = 0;
-    // the left chain takes a snapshot at every new offset: the offsets T[k0 + i] are fetched 32 at a
-    // time (one coalesced load per 32 snapshots instead of one dependent L2 round trip per snapshot)
-    int tb = -1;
-    double tc = 0.0;
-    auto snap_row = [&](int i) -> long long {
-        if (ch.kind != 1) return gw_snap_row(c, ch, i);
-        if ((i >> 5) != tb) {
-            tb = i >> 5;
-            const int64_t k = (int64_t)c.plan->k0 + 32 * tb + lane;
-            tc = k < c.g->kmax ? __ldg(c.g->T + k) : 0.0;
+    // Snapshot rows, relative to ch.pos: lane l computes the row of snapshot 32 b + l once per batch b,
+    // the chain takes them by shuffle, always ONE snapshot ahead, so that neither the offset table nor
+    // the double -> integer conversion sits between two segments of the serial add chain.
+    int relbatch = -1, myrel = 0;
+    auto fetch = [&](int i) -> int {
+        if (i >= ch.nsnap) return INT_MAX;
+        if ((i >> 5) != relbatch) {
+            relbatch = i >> 5;
+            const int ii = 32 * relbatch + lane;
+            long long row = 0;
+            if (ii < ch.nsnap)
+                row = ch.kind == 1 ? c.base + (int64_t)(c.start + gw_Tp(c.g, (int64_t)c.plan->k0 + ii))
+                                   : gw_snap_row(c, ch, ii);
+            myrel = ii < ch.nsnap ? (int)(row - ch.pos) : INT_MAX;
         }
-        return c.base + (int64_t)(c.start + __shfl_sync(0xffffffffu, tc, i & 31));
+        return __shfl_sync(0xffffffffu, myrel, i & 31);
     };
-    long long snap_abs = LLONG_MAX, rb_abs = 0;
+    int snap_cur = INT_MAX, snap_nxt = INT_MAX;      // rows relative to ch.pos
+    long long rb_abs = 0;
     auto store_snap = [&]() {
         float* dst = gw_snap_dst(c, ch, si);
         dst[lane] = s0;
         if (second) dst[lane + 32] = s1;
         ++si;
-        snap_abs = si < ch.nsnap ? snap_row(si) : LLONG_MAX;
+        snap_cur = snap_nxt;
+        snap_nxt = fetch(si + 1);
     };
     if (active) {
         if (ch.init) {                               // written by another CTA one wave ago: L2
             s0 = __ldcg(ch.init + lane);
             if (second) s1 = __ldcg(ch.init + 32 + lane);
         }
-        rb_abs = snap_row(ch.nsnap - 1);             // last row + 1
-        snap_abs = snap_row(0);
-        while (si < ch.nsnap && snap_abs <= ch.pos) store_snap();
+        rb_abs = ch.pos + fetch(ch.nsnap - 1);       // last row + 1
+        snap_cur = fetch(0);
+        snap_nxt = fetch(1);
+        while (si < ch.nsnap && snap_cur <= 0) store_snap();
         if (si >= ch.nsnap) active = false;
     }
     if (lane == 0) {
-        range[2 * warp] = active ? ch.pos : LLONG_MAX;
-        range[2 * warp + 1] = active ? rb_abs : LLONG_MIN;
+        range[2 * cw] = active ? ch.pos : LLONG_MAX;
+        range[2 * cw + 1] = active ? rb_abs : LLONG_MIN;
     }
-    __syncthreads();
+    gw_chain_sync();
     long long A = LLONG_MAX, B = LLONG_MIN;
 #pragma unroll
-    for (int w = 0; w < GW_WARPS; ++w) {
+    for (int w = 0; w < GW_CHAIN_WARPS; ++w) {
         A = range[2 * w] < A ? range[2 * w] : A;
         B = range[2 * w + 1] > B ? range[2 * w + 1] : B;
     }
-    __syncthreads();                                 // `range` may be rewritten by the next round
+    gw_chain_sync();                                 // `range` may be rewritten by the next round
     if (!(A < B)) return;
     A &= ~3LL;                                       // 16-byte aligned start of the stream
     const int nst = (int)((B - A + GW_RING_ROWS - 1) / GW_RING_ROWS);
@@ -261,18 +277,19 @@ __device__ __forceinline__ void gw_sum_round(const GwChainCtx& c, const GwChain&
         if (nb > (long long)(GW_STAGE_FLOATS * sizeof(float))) nb = GW_STAGE_FLOATS * sizeof(float);
         return (unsigned)(nb & ~15LL);
     };
-    auto issue = [&](int i) {                        // thread 0 only
+    const bool issuer = cw == 0 && lane == 0;
+    auto issue = [&](int i) {                        // one thread only
         const int s = i % GW_RING_STAGES;
         const unsigned nb = stage_bytes(i);
         mbar_expect_tx(bars + s, nb);
         bulk_g2s(ring + s * GW_STAGE_FLOATS, x + (A + (long long)i * GW_RING_ROWS) * D39, nb, bars + s);
     };
-    if (threadIdx.x == 0)
+    if (issuer)
         for (int p = 0; p < GW_RING_STAGES && p < nst; ++p) issue(p);
     // positions relative to A from here on (a batch spans far less than 2^31 rows)
-    int pos = active ? (int)(ch.pos - A) : 0;
+    const int org = active ? (int)(ch.pos - A) : 0;          // snapshot rows are relative to ch.pos
+    int pos = org;
     const int rb = active ? (int)(rb_abs - A) : 0;
-    int snap = active ? (int)(snap_abs - A) : INT_MAX;
     if (active) dbg_rows += rb - pos;
     for (int i = 0; i < nst; ++i) {
         const int s = i % GW_RING_STAGES;
@@ -288,21 +305,35 @@ __device__ __forceinline__ void gw_sum_round(const GwChainCtx& c, const GwChain&
             const float* buf = ring + s * GW_STAGE_FLOATS + lane - r0 * D39;         // buf[r * D39] = row r
             int r = pos > r0 ? pos : r0;
             for (;;) {
-                if (r == snap) {                                 // the sum of the rows below `snap`
-                    store_snap();
-                    snap = snap_abs == LLONG_MAX ? INT_MAX : (int)(snap_abs - A);
-                    continue;
-                }
+                const int snap = snap_cur == INT_MAX ? INT_MAX : snap_cur + org;
+                if (r == snap) { store_snap(); continue; }       // the sum of the rows below `snap`
                 if (r >= hi) break;
                 const int seg = snap < hi ? snap : hi;
                 const int sseg = seg < safe ? seg : safe;
-                for (; r + 8 <= sseg; r += 8) {                  // loads first, then the serial add chain
-                    float u[8], v[8];
-                    const float* row = buf + r * D39;
+                if (r + 8 <= sseg) {                             // 8 rows at a time; the loads of the next 8 rows
+                    float ua[8], va[8], ub[8], vb[8];            // are in flight while the serial add chain runs
+                    auto load8 = [&](float (&u)[8], float (&v)[8], int rr) {
+                        const float* row = buf + rr * D39;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) { u[q] = row[q * D39]; v[q] = second ? row[q * D39 + 32] : 0.f; }
+                        for (int q = 0; q < 8; ++q) { u[q] = row[q * D39]; v[q] = second ? row[q * D39 + 32] : 0.f; }
+                    };
+                    auto add8 = [&](const float (&u)[8], const float (&v)[8]) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) { s0 = __fadd_rn(s0, u[q]); s1 = __fadd_rn(s1, v[q]); }
+                        for (int q = 0; q < 8; ++q) { s0 = __fadd_rn(s0, u[q]); s1 = __fadd_rn(s1, v[q]); }
+                    };
+                    load8(ua, va, r);
+                    for (;;) {
+                        bool more = r + 16 <= sseg;
+                        if (more) load8(ub, vb, r + 8);
+                        add8(ua, va);
+                        r += 8;
+                        if (!more) break;
+                        more = r + 16 <= sseg;
+                        if (more) load8(ua, va, r + 8);
+                        add8(ub, vb);
+                        r += 8;
+                        if (!more) break;
+                    }
                 }
                 for (; r < sseg; ++r) {
                     s0 = __fadd_rn(s0, buf[r * D39]);
@@ -316,8 +347,8 @@ __device__ __forceinline__ void gw_sum_round(const GwChainCtx& c, const GwChain&
             }
             pos = hi;
         }
-        __syncthreads();                                         // stage i has been consumed by every warp
-        if (threadIdx.x == 0 && i + GW_RING_STAGES < nst) issue(i + GW_RING_STAGES);
+        gw_chain_sync();                                         // stage i has been consumed by every chain warp
+        if (issuer && i + GW_RING_STAGES < nst) issue(i + GW_RING_STAGES);
     }
 }
 
@@ -337,13 +368,13 @@ __device__ __forceinline__ GwChain gw_make_chain(const GwChainCtx& c, int ct, in
             ch.pos = plan.chain_row;
             ch.init = c.sum_right + ((int64_t)plan.chain_parity * g.kcap + plan.chain_base + k) * VS;
         } else {
-            ch.pos = c.base + (int64_t)(c.start + __ldg(g.T + k));
+            ch.pos = c.base + (int64_t)(c.start + gw_Tp(&g, k));
             ch.init = nullptr;
         }
     } else if (plan.mode == 0) {                            // coarse left chain
         ch.kind = 1; ch.a = 0; ch.w0 = 0; ch.nsnap = plan.nL;
         if (plan.k0 > 0) {
-            ch.pos = c.base + (int64_t)(c.start + __ldg(g.T + plan.k0 - 1));
+            ch.pos = c.base + (int64_t)(c.start + gw_Tp(&g, plan.k0 - 1));
             ch.init = c.sum_left + (int64_t)(plan.k0 - 1) * VS;
         } else {
             ch.pos = s0; ch.init = nullptr;
@@ -357,10 +388,10 @@ __device__ __forceinline__ GwChain gw_make_chain(const GwChainCtx& c, int ct, in
         const long long m0 = c.base + (int64_t)(c.start + plan.fi[0]);
         int kk = plan.pend_bk - 1;                          // nearest cached offset at or below m0
         if (kk >= left_valid) kk = left_valid - 1;
-        while (kk + 1 < left_valid && c.base + (int64_t)(c.start + __ldg(g.T + kk + 1)) <= m0) ++kk;
-        while (kk >= 0 && c.base + (int64_t)(c.start + __ldg(g.T + kk)) > m0) --kk;
+        while (kk + 1 < left_valid && c.base + (int64_t)(c.start + gw_Tp(&g, kk + 1)) <= m0) ++kk;
+        while (kk >= 0 && c.base + (int64_t)(c.start + gw_Tp(&g, kk)) > m0) --kk;
         if (kk >= 0) {
-            ch.pos = c.base + (int64_t)(c.start + __ldg(g.T + kk));
+            ch.pos = c.base + (int64_t)(c.start + gw_Tp(&g, kk));
             ch.init = c.sum_left + (int64_t)kk * VS;
         } else {
             ch.pos = s0; ch.init = nullptr;
@@ -391,6 +422,32 @@ __device__ __forceinline__ double gw_kl2_distance(const double* sideL, const dou
     return __dadd_rn(__dmul_rn(0.5, t1), __dmul_rn(0.5, t2));
 }
 
+// candidate offset k: the host table, or its closed form when the host found the
+// table to BE minfeas + k * istep exactly (dyadic frame rates such as 100 or 125 fps)
+__device__ __forceinline__ double gw_T(const GwDev& g, int64_t k) {
+    return g.t_exact ? __dadd_rn(g.minfeas, __dmul_rn((double)k, g.istep)) : __ldg(g.T + k);
+}
+// count of k with T[k] < lim (T strictly increasing), from an arithmetic guess
+__device__ __forceinline__ int gw_count_below(const GwDev& g, double lim) {
+    double q = (lim - g.minfeas) / g.istep;
+    int64_t k = q > 0.0 ? (int64_t)q : 0;
+    if (k > g.kmax) k = g.kmax;
+    while (k < g.kmax && gw_T(g, k) < lim) ++k;
+    while (k > 0 && !(gw_T(g, k - 1) < lim)) --k;
+    return (int)k;
+}
+
+constexpr int GW_SLOT_BLOCK = 64;       // window records are claimed 64 at a time
+
+// thread-0 state of one chain (the reference's loop variables, CD:189-200)
+struct GwState {
+    double start, end, ws, dws;
+    int left_valid, seq, coarse_waves;
+    bool done, want_fine;
+    double pend_e, pend_maxi, pend_maxd;
+    int pend_ncand, pend_ninf;
+};
+
 template <bool KL2>
 __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
     extern __shared__ __align__(16) unsigned char gw_smem[];
@@ -400,6 +457,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
     const int group = blockIdx.x / g.group_ctas;
     const int rank = blockIdx.x - group * g.group_ctas;      // CTA rank in its group
     const int gwarps = g.group_ctas * GW_WARPS;
+    const bool is_bic = !KL2 && g.metric == SPKDIAR_BIC;
     const int rterms = KL2 ? 1 : (g.metric == SPKDIAR_GLR ? 2 : 1);
     double* left = g.left + (int64_t)group * g.kmax;
     double* right = g.right + (int64_t)group * 2 * g.bmax * g.kmax * rterms;
@@ -428,154 +486,173 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
     unsigned long long bar_target = 0;
     int wave = 0;               // parity source for the double-buffered term arrays
     int chain_pub = 0;          // parity of the published next-chain slot
+    unsigned long long slot_next = 0, slot_end = 0;     // claimed output slots (rank 0, thread 0)
 
     long long t_plan = 0, t_eval = 0, t_bar = 0, t_dec = 0, n_wave = 0, n_task = 0, t_e1 = 0, t_e2 = 0;
-    long long n_rows = 0, t_wait = 0;
+    long long n_rows = 0, t_wait = 0, t_last_chain = 0;
     long long t_chain = 0;      // KL2: cycles of warp 0 in the sum chains / of warp 1 in the sides
+
+    // ---- warp 0: describe the next wave in `plan` from the chain state.  The state is kept
+    // identical in all 32 lanes; lane w works on window w of the batch, the batch cut and the
+    // task offsets are warp scans - no serial walk over shared memory. ----
+    auto plan_wave = [&](GwState& st, double n) {
+        if (lane == 0) {
+            plan.parity = wave & 1;
+            plan.side_next = 0;
+            plan.start = st.start;
+            plan.left_valid = st.left_valid;
+            plan.mode = st.done ? 2 : (st.want_fine ? 1 : 0);
+        }
+        if (st.done) return;
+        if (st.want_fine) {
+            // fine-tune offsets, CD:235-251: i = maxi - istep; while i < maxi + istep: ...; i += 1
+            double i = st.pend_maxi - g.istep;
+            const double endtune = st.pend_maxi + g.istep;
+            int nJ = 0;
+            while (i < endtune && nJ < GW_JMAX) { if ((nJ & 31) == lane) plan.fi[nJ] = i; ++nJ; i += 1; }
+            if (lane == 0) {
+                plan.nJ = nJ;
+                plan.nW = 1;
+                plan.e[0] = st.pend_e;
+                plan.ntask = nJ * (KL2 ? 2 : (g.metric == SPKDIAR_GLR ? 3 : 2));
+            }
+            return;
+        }
+        // the growth schedule of `end` while no change is found, CD:273-284 (every lane, in registers)
+        double e = st.end, w_ = st.ws, dw = st.dws;
+        double my_e = 0.0, my_eaft = 0.0, my_wsa = 0.0, my_dwsa = 0.0;
+        int my_last = 0, nW = 0;
+        // KL2 speculates less right after a change: the sum chains of a batch cost rows x offsets,
+        // i.e. grow with the square of the depth, and most changes show within a few windows
+        int depth = g.bmax;
+        if (KL2 && g.bmax > 1) depth = st.coarse_waves == 0 ? g.kl2_depth[0] : (st.coarse_waves == 1 ? g.kl2_depth[1] : g.kl2_depth[2]);
+        for (int w = 0; w < depth; ++w) {
+            if (lane == w) my_e = e;
+            nW = w + 1;
+            int last = 0;
+            if (e + w_ <= n) {
+                e += w_;
+                if (w_ < g.winstep) { w_ += dw; dw *= 2; }
+                if (w_ > g.winstep) w_ = g.winstep;
+            } else if (e != n) {
+                e = n;
+            } else {
+                last = 1;
+            }
+            if (lane == w) { my_eaft = e; my_wsa = w_; my_dwsa = dw; my_last = last; }
+            if (last) break;
+        }
+        const bool in = lane < nW;
+        const int Kw = in ? gw_count_below(g, my_e - st.start - g.minfeas) : 0;                 // CD:204
+        int prevK = __shfl_up_sync(0xffffffffu, Kw, 1);
+        if (lane == 0 || prevK < st.left_valid) prevK = st.left_valid;
+        const int newl = Kw > prevK ? Kw - prevK : 0;
+        const int unit = in ? Kw * rterms : 0;
+        int tsc = in ? unit + newl + (is_bic ? 1 : 0) : 0, ksc = unit;     // inclusive scans: tasks, right terms
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tv = __shfl_up_sync(0xffffffffu, tsc, o), kv = __shfl_up_sync(0xffffffffu, ksc, o);
+            if (lane >= o) { tsc += tv; ksc += kv; }
+        }
+        // cut the batch to the group's one-round capacity (always keep window 0)
+        const unsigned over = __ballot_sync(0xffffffffu, in && lane > 0 && tsc > gwarps);
+        const int nWc = over ? __ffs(over) - 1 : nW;
+        const int klast = __shfl_sync(0xffffffffu, Kw, nWc - 1);
+        const int kmaxw = klast > st.left_valid ? klast : st.left_valid;
+        const int nL = kmaxw - st.left_valid;
+        const int off0 = KL2 ? 0 : nL + (is_bic ? nWc : 0);
+        if (lane < nWc) {
+            plan.e[lane] = my_e; plan.e_after[lane] = my_eaft; plan.ws_after[lane] = my_wsa;
+            plan.dws_after[lane] = my_dwsa; plan.last[lane] = my_last; plan.K[lane] = Kw;
+            plan.sec[lane] = off0 + ksc - unit;
+            if (lane == nWc - 1) { plan.sec[nWc] = off0 + ksc; plan.ntask = (KL2 ? nL : 0) + off0 + ksc; }
+        }
+        if (lane == 0) { plan.nW = nWc; plan.k0 = st.left_valid; plan.nL = nL; plan.kmaxw = kmaxw; }
+    };
+    // claim `cnt` consecutive output slots (warp 0; every lane keeps the same cursor)
+    auto claim_slots = [&](int cnt) -> unsigned long long {
+        if (slot_end - slot_next < (unsigned long long)cnt) {
+            unsigned long long b0 = 0;
+            if (lane == 0) b0 = atomicAdd(g.nwin, (unsigned long long)GW_SLOT_BLOCK);
+            slot_next = __shfl_sync(0xffffffffu, b0, 0);
+            slot_end = slot_next + GW_SLOT_BLOCK;
+        }
+        const unsigned long long s0 = slot_next;
+        slot_next += cnt;
+        return s0;
+    };
+
     int chain = group;
     while (chain < g.nchain) {
-        // ---- chain state (identical in thread 0 of every CTA of the group) ----
         const int64_t base = g.seg_a[chain];
         const int64_t nfr = g.seg_b[chain] - base;
         const double n = (double)nfr;
-        double start = 0.0;
-        double end = start + g.winsize * 2;
-        double ws = g.minfeas, dws = g.deltaws;
-        int left_valid = 0;
-        int seq = 0;
-        bool done = !(end <= n);
-        // pending positive window (between the coarse and the fine wave)
-        double pend_e = 0.0, pend_maxi = 0.0, pend_maxd = 0.0;
-        int pend_ncand = 0, pend_ninf = 0;
-        bool want_fine = false;
-        int coarse_waves = 0;       // coarse waves since `start` last moved (thread 0)
-        if (threadIdx.x == 0) plan.chain_valid = 0;
+        GwState st;
+        st.start = 0.0;
+        st.end = st.start + g.winsize * 2;
+        st.ws = g.minfeas; st.dws = g.deltaws;
+        st.left_valid = 0; st.seq = 0; st.coarse_waves = 0;
+        st.done = !(st.end <= n);
+        st.want_fine = false;
+        st.pend_e = st.pend_maxi = st.pend_maxd = 0.0; st.pend_ncand = st.pend_ninf = 0;
+        if (warp == 0) {
+            if (lane == 0) plan.chain_valid = 0;
+            plan_wave(st, n);
+        }
+        __syncthreads();
 
-        while (!done) {
-            // ================= PLAN =================
-            const long long c0 = clock64();
-            const int parity = wave & 1;
-            if (threadIdx.x == 0) {
-                plan.parity = parity;
-                plan.rterms = rterms;
-                if (!want_fine) {
-                    plan.mode = 0;
-                    double e = end, w_ = ws, dw = dws;
-                    int nW = 0;
-                    // KL2 speculates less right after a change: the sum chains of a batch cost rows x offsets,
-                    // i.e. grow with the square of the depth, and most changes show within a few windows
-                    int depth = g.bmax;
-                    if (KL2 && g.bmax > 1) depth = coarse_waves == 0 ? 4 : (coarse_waves == 1 ? 8 : g.bmax);
-                    for (int w = 0; w < depth; ++w) {
-                        plan.e[w] = e;
-                        nW = w + 1;
-                        // negative-branch growth, CD:273-284
-                        int last = 0;
-                        if (e + w_ <= n) {
-                            e += w_;
-                            if (w_ < g.winstep) { w_ += dw; dw *= 2; }
-                            if (w_ > g.winstep) w_ = g.winstep;
-                        } else if (e != n) {
-                            e = n;
-                        } else {
-                            last = 1;
-                        }
-                        plan.e_after[w] = e; plan.ws_after[w] = w_; plan.dws_after[w] = dw; plan.last[w] = last;
-                        if (last) break;
-                    }
-                    plan.nW = nW;
-                } else {
-                    plan.mode = 1;
-                    // fine-tune offsets, CD:235-251: i = maxi - istep; while i < maxi + istep: ...; i += 1
-                    double i = pend_maxi - g.istep;
-                    const double endtune = pend_maxi + g.istep;
-                    int nJ = 0;
-                    while (i < endtune && nJ < GW_JMAX) { plan.fi[nJ++] = i; i += 1; }
-                    plan.nJ = nJ;
-                    plan.nW = 1;
-                    plan.e[0] = pend_e;
-                }
-            }
-            __syncthreads();
-            if (plan.mode == 0) {
-                if (threadIdx.x < plan.nW) {
-                    const double lim = plan.e[threadIdx.x] - start - g.minfeas;     // CD:204
-                    plan.K[threadIdx.x] = gw_count_below(g.T, g.kmax, lim, g.minfeas, g.istep);
-                }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    // cut the batch to the group's one-round capacity (always keep window 0)
-                    int nW = 0, tasks = 0, kmaxw = left_valid;
-                    for (int w = 0; w < plan.nW; ++w) {
-                        const int newl = plan.K[w] > kmaxw ? plan.K[w] - kmaxw : 0;
-                        const int t = plan.K[w] * rterms + newl + ((!KL2 && g.metric == SPKDIAR_BIC) ? 1 : 0);
-                        if (w > 0 && tasks + t > gwarps) break;
-                        tasks += t;
-                        if (plan.K[w] > kmaxw) kmaxw = plan.K[w];
-                        nW = w + 1;
-                    }
-                    plan.nW = nW;
-                    plan.k0 = left_valid;
-                    plan.nL = kmaxw - left_valid;
-                    plan.kmaxw = kmaxw;
-                    if (KL2) {
-                        // sec = candidate slots of window w; side tasks: nL lefts, then one right per slot
-                        int off = 0;
-                        for (int w = 0; w < nW; ++w) { plan.sec[w] = off; off += plan.K[w]; }
-                        plan.sec[nW] = off;
-                        plan.ntask = plan.nL + off;
-                    } else {
-                        int off = plan.nL + (g.metric == SPKDIAR_BIC ? nW : 0);
-                        for (int w = 0; w < nW; ++w) { plan.sec[w] = off; off += plan.K[w] * rterms; }
-                        plan.sec[nW] = off;
-                        plan.ntask = off;
-                    }
-                }
-            } else if (threadIdx.x == 0) {
-                plan.ntask = plan.nJ * (KL2 ? 2 : (g.metric == SPKDIAR_GLR ? 3 : 2));
-            }
-            __syncthreads();
-
+        while (plan.mode != 2) {
             // ================= EVALUATE =================
             const long long c1 = clock64();
+            const int parity = plan.parity;
+            const double start = plan.start;
+            const int left_valid = plan.left_valid;
             const int64_t s0 = base + (int64_t)start;
             if (KL2) {
                 const long long k0c = clock64();
-                {
-                    // ---- sum chains: chain ct belongs to CTA ct % group_ctas, twelve per round ----
+                if (warp >= GW_CHAIN_WARP0) {
+                    // ---- sum chains: chain ct belongs to CTA ct % group_ctas, four per round ----
                     GwChainCtx cc{&g, &plan, base, start, ksum_left, ksum_right, ksum_fine};
+                    const int cw = warp - GW_CHAIN_WARP0;
                     const int nright = plan.mode == 0 ? plan.kmaxw : plan.nJ;
                     const int nct = nright + ((plan.mode == 0 ? plan.nL : plan.nJ) > 0 ? 1 : 0);
-                    for (int c0 = rank; c0 < nct; c0 += g.group_ctas * GW_WARPS) {
-                        const int ct = c0 + warp * g.group_ctas;
+                    for (int c0 = rank; c0 < nct; c0 += g.group_ctas * GW_CHAIN_WARPS) {
+                        const int ct = c0 + cw * g.group_ctas;
                         GwChain ch;
                         ch.kind = 0; ch.a = 0; ch.w0 = 0; ch.nsnap = 0; ch.pos = 0; ch.init = nullptr;
                         if (ct < nct) ch = gw_make_chain(cc, ct, nright, left_valid, s0);
-                        gw_sum_round(cc, ch, ct < nct && ch.nsnap > 0, range, ring, ring_bar, ring_phase, warp, lane,
+                        gw_sum_round(cc, ch, ct < nct && ch.nsnap > 0, range, ring, ring_bar, ring_phase, cw, lane,
                                      n_rows, t_wait);
                     }
-                    if (warp == 0) t_chain += clock64() - k0c;
+                    if (cw == 0) { t_chain += clock64() - k0c; t_last_chain = clock64() - k0c; }
+                    if (g.trace && n_wave == 1 && lane == 0) g.trace[8 * 4096 + 16 * blockIdx.x + 12 + cw] = clock64() - k0c;
                 }
                 {
-                    // ---- sides: diag(S), diag(S^-1) of one window per task ----
+                    // ---- sides: diag(S), diag(S^-1) of one window per task.  The CTA owns a contiguous
+                    // chunk of tasks (see below); its warps claim them one by one, the chain warps join
+                    // when their sums are done ----
                     const long long k2c = clock64();
                     GwKl2Warp& own = kwarps[warp];
-                    const int chunk = (plan.ntask + g.group_ctas - 1) / g.group_ctas;     // contiguous, see below
+                    const int chunk = (plan.ntask + g.group_ctas - 1) / g.group_ctas;
                     const int id_end = (rank + 1) * chunk < plan.ntask ? (rank + 1) * chunk : plan.ntask;
-                    for (int id = rank * chunk + warp; id < id_end; id += GW_WARPS) {
+                    for (;;) {
+                        int id = 0;
+                        if (lane == 0) id = rank * chunk + atomicAdd(&plan.side_next, 1);
+                        id = __shfl_sync(0xffffffffu, id, 0);
+                        if (id >= id_end) break;
                         int64_t ra, rb;
                         double* dst;
                         if (plan.mode == 0) {
                             if (id < plan.nL) {                                 // left side of a new offset
                                 const int k = plan.k0 + id;
-                                ra = s0; rb = base + (int64_t)(start + __ldg(g.T + k));
+                                ra = s0; rb = base + (int64_t)(start + gw_T(g, k));
                                 dst = kside_left + (int64_t)k * KS;
                             } else {                                            // right side of candidate slot t
                                 const int t = id - plan.nL;
                                 int w = 0;
                                 while (t >= plan.sec[w + 1]) ++w;
                                 const int k = t - plan.sec[w];
-                                ra = base + (int64_t)(start + __ldg(g.T + k));
+                                ra = base + (int64_t)(start + gw_T(g, k));
                                 rb = base + (int64_t)plan.e[w];
                                 dst = kside_right + ((int64_t)parity * g.kcap + t) * KS;
                             }
@@ -588,11 +665,17 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                         }
                         kl2_side_one(WinSrc(g.st, ra, rb, REC), own, dst, dst + VS, lane);
                     }
-                    if (warp == 1) t_chain += clock64() - k2c;
+                    if (warp == 0) t_chain += clock64() - k2c;
                 }
                 const long long k1c = clock64();
+                if (g.trace && n_wave == 1 && lane == 0) g.trace[8 * 4096 + 16 * blockIdx.x + warp] = k1c - k0c;
                 gw_group_barrier(bar, bar_target, g.group_ctas);
                 t_e1 += k1c - k0c; t_e2 += clock64() - k1c;
+                if (g.trace && blockIdx.x == 0 && threadIdx.x == 0 && n_wave < 4096) {
+                    long long* tr = g.trace + 8 * n_wave;
+                    tr[0] = plan.mode; tr[1] = plan.nW; tr[2] = plan.ntask; tr[3] = plan.mode == 0 ? plan.kmaxw : plan.nJ;
+                    tr[4] = k1c - k0c; tr[5] = clock64() - k1c; tr[6] = (long long)(plan.e[plan.nW - 1] - start); tr[7] = t_last_chain;
+                }
                 // ---- distances: one warp per candidate ----
                 const int ncand = plan.mode == 0 ? plan.sec[plan.nW] : plan.nJ;
                 for (int t = warp * g.group_ctas + rank; t < ncand; t += gwarps) {
@@ -601,7 +684,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                         int w = 0;
                         while (t >= plan.sec[w + 1]) ++w;
                         const int k = t - plan.sec[w];
-                        mm = base + (int64_t)(start + __ldg(g.T + k));
+                        mm = base + (int64_t)(start + gw_T(g, k));
                         ee = base + (int64_t)plan.e[w];
                         sl = kside_left + (int64_t)k * KS;              ml = ksum_left + (int64_t)k * VS;
                         sr = kside_right + ((int64_t)parity * g.kcap + t) * KS;
@@ -631,10 +714,10 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     int term = 0;
                     double* dst = nullptr;
                     if (plan.mode == 0) {
-                        const int npool = g.metric == SPKDIAR_BIC ? plan.nW : 0;
+                        const int npool = is_bic ? plan.nW : 0;
                         if (id < plan.nL) {                         // left term of a new coarse offset
                             const int k = plan.k0 + id;
-                            mm = base + (int64_t)(start + __ldg(g.T + k));
+                            mm = base + (int64_t)(start + gw_T(g, k));
                             ee = mm; term = 0; dst = left + k;
                         } else if (id < plan.nL + npool) {          // pooled term of window w (BIC)
                             const int w = id - plan.nL;
@@ -645,7 +728,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                             while (id >= plan.sec[w + 1]) ++w;
                             const int r = id - plan.sec[w];
                             const int k = r / rterms, sub = r - k * rterms;
-                            mm = base + (int64_t)(start + __ldg(g.T + k));
+                            mm = base + (int64_t)(start + gw_T(g, k));
                             ee = base + (int64_t)plan.e[w];
                             term = sub == 0 ? 1 : 2;
                             dst = right + (((int64_t)parity * g.bmax + w) * g.kmax + k) * rterms + sub;
@@ -670,158 +753,160 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
             const long long c3 = clock64();
             ++wave;
 
-            // ================= DECIDE =================
-            if (plan.mode == 0) {
-                if (warp < plan.nW) {
-                    const int w = warp;
-                    const int64_t e0 = (int64_t)plan.e[w];
-                    const int64_t s0r = (int64_t)start;
-                    const double pl = (!KL2 && g.metric == SPKDIAR_BIC) ? __ldcg(pooled + parity * GW_BMAX + w) : 0.0;
-                    const double pen = (!KL2 && g.metric == SPKDIAR_BIC) ? bic_pen(g.lambda, (double)(e0 - s0r)) : 0.0;
-                    double bd = GW_NEG_INIT; int bk = -1; int ninf = 0;
-                    for (int k = lane; k < plan.K[w]; k += 32) {
-                        const int64_t m = (int64_t)(start + __ldg(g.T + k));
-                        const double N1 = (double)(m - s0r), N2 = (double)(e0 - m);
-                        const double* rp = right + (((int64_t)parity * g.bmax + w) * g.kmax + k) * rterms;
-                        double d;
-                        if (KL2) d = __ldcg(rp);
-                        else if (g.metric == SPKDIAR_BIC) d = bic_combine_pen(N1, N2, __ldcg(left + k), __ldcg(rp), pl, pen);
-                        else d = glr_combine(N1, N2, __ldcg(left + k), __ldcg(rp), __ldcg(rp + 1));
-                        if (d == d_inf() || d == -d_inf()) ++ninf;          // CD:219-220
-                        else if (d > bd) { bd = d; bk = k; }                // CD:215-217 (strict, first wins)
-                    }
+            // ================= DECIDE: best candidate per window, one warp per window =================
+            const int nwin = plan.mode == 0 ? plan.nW : 1;
+            if (warp < nwin) {
+                const int w = warp;
+                const bool coarse = plan.mode == 0;
+                const int ncand = coarse ? plan.K[w] : plan.nJ;
+                const int64_t e0 = (int64_t)plan.e[w];
+                const int64_t s0r = (int64_t)start;
+                const double* f0 = fine + (int64_t)parity * 3 * GW_JMAX;
+                const double pl = !is_bic ? 0.0 : (coarse ? __ldcg(pooled + parity * GW_BMAX + w) : plan.pend_pl);
+                const double pen = is_bic ? bic_pen(g.lambda, (double)(e0 - s0r)) : 0.0;
+                double bd = GW_NEG_INIT; int bk = -1; int ninf = 0;
+                for (int c0 = 0; c0 < ncand; c0 += 128) {           // four candidates per lane: loads first
+                    double off[4], t0[4], t1[4], t2[4];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-                        const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-                        ninf += __shfl_xor_sync(0xffffffffu, ninf, o);
-                        if (ok >= 0 && (bk < 0 || od > bd || (od == bd && ok < bk))) { bd = od; bk = ok; }
-                    }
-                    if (lane == 0) { plan.bd[w] = bd; plan.bk[w] = bk; plan.ninf[w] = ninf; }
-                }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    int kmaxw = left_valid;
-                    // negative windows ahead of the first positive one: their records take
-                    // consecutive slots claimed with ONE atomic
-                    int nneg = 0;
-                    for (int w = 0; w < plan.nW; ++w) {
-                        if (plan.bd[w] > g.threshold && plan.bk[w] >= 0) break;
-                        ++nneg;
-                        if (plan.last[w]) break;
-                    }
-                    unsigned long long slot = 0;
-                    if (rank == 0 && nneg > 0) slot = atomicAdd(g.nwin, (unsigned long long)nneg);
-                    for (int w = 0; w < plan.nW; ++w) {
-                        if (plan.K[w] > kmaxw) kmaxw = plan.K[w];
-                        const double maxd = plan.bd[w];
-                        const double maxi = plan.bk[w] >= 0 ? __ldg(g.T + plan.bk[w]) : 0.0;
-                        const bool positive = maxd > g.threshold && plan.bk[w] >= 0;       // CD:230
-                        if (positive) {
-                            want_fine = true;
-                            pend_e = plan.e[w]; pend_maxi = maxi; pend_maxd = maxd;
-                            pend_ncand = plan.K[w]; pend_ninf = plan.ninf[w];
-                            plan.pend_bk = plan.bk[w];
-                            if (!KL2 && g.metric == SPKDIAR_BIC) plan.pend_pl = __ldcg(pooled + parity * GW_BMAX + w);
-                            end = plan.e[w];
-                            break;
-                        }
-                        if (rank == 0) {                                                    // negative window record
-                            if ((int64_t)slot < g.win_cap) {
-                                spkdiar_gw_window r;
-                                r.start = start; r.end = plan.e[w]; r.maxi = maxi; r.maxd = maxd;
-                                r.maxi_fine = 0.0; r.maxd_fine = 0.0; r.positive = 0; r.chain = chain;
-                                r.ncand = plan.bk[w] >= 0 ? plan.K[w] : -plan.K[w] - 1;
-                                r.ninf = plan.ninf[w]; r.seq = seq; r.pad = 0;
-                                g.win[slot] = r;
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = c0 + 32 * u + lane;
+                        off[u] = t0[u] = t1[u] = t2[u] = 0.0;
+                        if (k < ncand) {
+                            if (coarse) {
+                                const double* rp = right + (((int64_t)parity * g.bmax + w) * g.kmax + k) * rterms;
+                                off[u] = gw_T(g, k);
+                                t1[u] = __ldcg(rp);
+                                if (!KL2) t0[u] = __ldcg(left + k);
+                                if (!KL2 && !is_bic) t2[u] = __ldcg(rp + 1);
+                            } else {
+                                off[u] = plan.fi[k];
+                                t0[u] = __ldcg(f0 + k);
+                                if (!KL2) t1[u] = __ldcg(f0 + GW_JMAX + k);
+                                if (!KL2 && !is_bic) t2[u] = __ldcg(f0 + 2 * GW_JMAX + k);
                             }
-                            ++slot;
                         }
-                        ++seq;
-                        end = plan.e_after[w]; ws = plan.ws_after[w]; dws = plan.dws_after[w];
-                        if (plan.last[w]) { done = true; break; }
-                    }
-                    // every offset of the batch now has its left term / left side, and (KL2) a
-                    // running right sum that ends at the last window of the batch
-                    left_valid = plan.kmaxw;
-                    ++coarse_waves;
-                    if (KL2) {
-                        plan.chain_valid = plan.kmaxw;
-                        plan.chain_base = plan.sec[plan.nW - 1];
-                        plan.chain_parity = parity;
-                        plan.chain_row = base + (int64_t)plan.e[plan.nW - 1];
-                    }
-                    plan.mode = done ? 2 : (want_fine ? 1 : 0);
-                }
-            } else {
-                // fine-tune decision, CD:237-251: strict improvement over the coarse maximum, first wins
-                if (warp == 0) {
-                    const int64_t e0 = (int64_t)plan.e[0];
-                    const int64_t s0r = (int64_t)start;
-                    const double* f0 = fine + (int64_t)parity * 3 * GW_JMAX;
-                    const double pl = plan.pend_pl;
-                    const double pen = (!KL2 && g.metric == SPKDIAR_BIC) ? bic_pen(g.lambda, (double)(e0 - s0r)) : 0.0;
-                    double bd = GW_NEG_INIT; int bj = -1; int ninf = 0;
-                    for (int j = lane; j < plan.nJ; j += 32) {
-                        const int64_t m = (int64_t)(start + plan.fi[j]);
-                        const double N1 = (double)(m - s0r), N2 = (double)(e0 - m);
-                        double d;
-                        if (KL2) d = __ldcg(f0 + j);
-                        else if (g.metric == SPKDIAR_BIC) d = bic_combine_pen(N1, N2, __ldcg(f0 + j), __ldcg(f0 + GW_JMAX + j), pl, pen);
-                        else d = glr_combine(N1, N2, __ldcg(f0 + j), __ldcg(f0 + GW_JMAX + j), __ldcg(f0 + 2 * GW_JMAX + j));
-                        if (d == d_inf() || d == -d_inf()) ++ninf;
-                        else if (d > bd) { bd = d; bj = j; }
                     }
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-                        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-                        ninf += __shfl_xor_sync(0xffffffffu, ninf, o);
-                        if (oj >= 0 && (bj < 0 || od > bd || (od == bd && oj < bj))) { bd = od; bj = oj; }
-                    }
-                    if (lane == 0) { plan.bd[0] = bd; plan.bk[0] = bj; plan.ninf[0] = ninf; }
-                }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    double maxd = pend_maxd, maxi = pend_maxi;
-                    if (plan.bk[0] >= 0 && plan.bd[0] > pend_maxd) { maxd = plan.bd[0]; maxi = plan.fi[plan.bk[0]]; }
-                    if (rank == 0) {
-                        const unsigned long long slot = atomicAdd(g.nwin, 1ULL);
-                        if ((int64_t)slot < g.win_cap) {
-                            spkdiar_gw_window r;
-                            r.start = start; r.end = pend_e; r.maxi = pend_maxi; r.maxd = pend_maxd;
-                            r.maxi_fine = maxi; r.maxd_fine = maxd; r.positive = 1; r.chain = chain;
-                            r.ncand = pend_ncand; r.ninf = pend_ninf + plan.ninf[0]; r.seq = seq; r.pad = 0;
-                            g.win[slot] = r;
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = c0 + 32 * u + lane;
+                        if (k < ncand) {
+                            const int64_t m = (int64_t)(start + off[u]);
+                            const double N1 = (double)(m - s0r), N2 = (double)(e0 - m);
+                            double d;
+                            if (KL2) d = coarse ? t1[u] : t0[u];
+                            else if (is_bic) d = bic_combine_pen(N1, N2, t0[u], t1[u], pl, pen);
+                            else d = glr_combine(N1, N2, t0[u], t1[u], t2[u]);
+                            if (d == d_inf() || d == -d_inf()) ++ninf;          // CD:219-220
+                            else if (d > bd) { bd = d; bk = k; }                // CD:215-217 (strict, first wins)
                         }
                     }
-                    ++seq;
-                    want_fine = false;
-                    coarse_waves = 0;
-                    left_valid = 0;                                     // CD:256
-                    plan.chain_valid = 0;
-                    start += maxi;                                      // CD:263
-                    if (start + g.winsize * 2 <= n) {                   // CD:264-268
-                        end = start + g.winsize * 2;
-                        ws = g.minfeas; dws = g.deltaws;
-                    } else {
-                        done = true;                                    // CD:269-270
-                    }
-                    plan.mode = done ? 2 : 0;
                 }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                    const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                    ninf += __shfl_xor_sync(0xffffffffu, ninf, o);
+                    if (ok >= 0 && (bk < 0 || od > bd || (od == bd && ok < bk))) { bd = od; bk = ok; }
+                }
+                if (lane == 0) { plan.bd[w] = bd; plan.bk[w] = bk; plan.ninf[w] = ninf; plan.pl[w] = pl; }
             }
             __syncthreads();
-            // every thread follows thread 0's view of the chain state
-            done = plan.mode == 2;
-            want_fine = plan.mode == 1;
-            // `start`, `end`, ... live in thread 0; the others need start / left_valid for the next wave
-            if (threadIdx.x == 0) { plan.e_after[0] = start; plan.K[0] = left_valid; }
+            const long long c4 = clock64();
+
+            // ================= warp 0: apply the reference's decision rules, plan the next wave =================
+            if (warp == 0) {
+                if (plan.mode == 0) {
+                    // lane w looks at window w; windows count in order up to the first positive one
+                    // (it goes to the fine tune) or the first negative one that ends the chain
+                    const int nW = plan.nW;
+                    const bool in = lane < nW;
+                    const double bd = in ? plan.bd[lane] : 0.0;
+                    const int bk = in ? plan.bk[lane] : -1;
+                    const int ninfw = in ? plan.ninf[lane] : 0;
+                    const int Kw = in ? plan.K[lane] : 0;
+                    const double ew = in ? plan.e[lane] : 0.0, eaft = in ? plan.e_after[lane] : 0.0;
+                    const double wsa = in ? plan.ws_after[lane] : 0.0, dwsa = in ? plan.dws_after[lane] : 0.0;
+                    const double plw = in ? plan.pl[lane] : 0.0;
+                    const double maxi = bk >= 0 ? gw_T(g, bk) : 0.0;
+                    const bool pos = in && bd > g.threshold && bk >= 0;                        // CD:230
+                    const unsigned mpos = __ballot_sync(0xffffffffu, pos);
+                    const unsigned mlast = __ballot_sync(0xffffffffu, in && plan.last[in ? lane : 0] != 0);
+                    const int fpos = mpos ? __ffs(mpos) - 1 : 32, flast = mlast ? __ffs(mlast) - 1 : 32;
+                    const bool has_pos = fpos < nW && fpos <= flast;
+                    const int nneg = has_pos ? fpos : (flast + 1 < nW ? flast + 1 : nW);
+                    const bool fin = !has_pos && flast < nW;
+                    if (rank == 0 && nneg > 0) {                                               // negative window records
+                        const unsigned long long sb = claim_slots(nneg);
+                        if (lane < nneg && (int64_t)(sb + lane) < g.win_cap) {
+                            spkdiar_gw_window r;
+                            r.start = st.start; r.end = ew; r.maxi = maxi; r.maxd = bd;
+                            r.maxi_fine = 0.0; r.maxd_fine = 0.0; r.positive = 0; r.chain = chain;
+                            r.ncand = bk >= 0 ? Kw : -Kw - 1;
+                            r.ninf = ninfw; r.seq = st.seq + lane; r.pad = 0;
+                            g.win[sb + lane] = r;
+                        }
+                    }
+                    st.seq += nneg;
+                    if (nneg > 0) {
+                        st.end = __shfl_sync(0xffffffffu, eaft, nneg - 1);
+                        st.ws = __shfl_sync(0xffffffffu, wsa, nneg - 1);
+                        st.dws = __shfl_sync(0xffffffffu, dwsa, nneg - 1);
+                    }
+                    if (has_pos) {
+                        st.want_fine = true;
+                        st.pend_e = __shfl_sync(0xffffffffu, ew, fpos);
+                        st.pend_maxi = __shfl_sync(0xffffffffu, maxi, fpos);
+                        st.pend_maxd = __shfl_sync(0xffffffffu, bd, fpos);
+                        st.pend_ncand = __shfl_sync(0xffffffffu, Kw, fpos);
+                        st.pend_ninf = __shfl_sync(0xffffffffu, ninfw, fpos);
+                        st.end = st.pend_e;
+                        if (lane == fpos) { plan.pend_bk = bk; plan.pend_pl = plw; }
+                    }
+                    if (fin) st.done = true;
+                    // every offset of the batch now has its left term / left side, and (KL2) a
+                    // running right sum that ends at the last window of the batch
+                    st.left_valid = plan.kmaxw;
+                    ++st.coarse_waves;
+                    if (KL2 && lane == 0) {
+                        plan.chain_valid = plan.kmaxw;
+                        plan.chain_base = plan.sec[nW - 1];
+                        plan.chain_parity = parity;
+                        plan.chain_row = base + (int64_t)plan.e[nW - 1];
+                    }
+                } else {
+                    // fine-tune decision, CD:237-251: strict improvement over the coarse maximum, first wins
+                    double maxd = st.pend_maxd, maxi = st.pend_maxi;
+                    if (plan.bk[0] >= 0 && plan.bd[0] > st.pend_maxd) { maxd = plan.bd[0]; maxi = plan.fi[plan.bk[0]]; }
+                    if (rank == 0) {
+                        const unsigned long long sb = claim_slots(1);
+                        if (lane == 0 && (int64_t)sb < g.win_cap) {
+                            spkdiar_gw_window r;
+                            r.start = st.start; r.end = st.pend_e; r.maxi = st.pend_maxi; r.maxd = st.pend_maxd;
+                            r.maxi_fine = maxi; r.maxd_fine = maxd; r.positive = 1; r.chain = chain;
+                            r.ncand = st.pend_ncand; r.ninf = st.pend_ninf + plan.ninf[0]; r.seq = st.seq; r.pad = 0;
+                            g.win[sb] = r;
+                        }
+                    }
+                    ++st.seq;
+                    st.want_fine = false;
+                    st.coarse_waves = 0;
+                    st.left_valid = 0;                                  // CD:256
+                    if (lane == 0) plan.chain_valid = 0;
+                    st.start += maxi;                                   // CD:263
+                    if (st.start + g.winsize * 2 <= n) {                // CD:264-268
+                        st.end = st.start + g.winsize * 2;
+                        st.ws = g.minfeas; st.dws = g.deltaws;
+                    } else {
+                        st.done = true;                                 // CD:269-270
+                    }
+                }
+                __syncwarp();                                           // reads of the old plan before it is rewritten
+                plan_wave(st, n);
+            }
             __syncthreads();
-            start = plan.e_after[0];
-            left_valid = plan.K[0];
-            __syncthreads();
-            t_plan += c1 - c0; t_eval += c2 - c1; t_bar += c3 - c2; t_dec += clock64() - c3; ++n_wave; n_task += plan.ntask;
+            t_eval += c2 - c1; t_bar += c3 - c2; t_dec += c4 - c3; t_plan += clock64() - c4; ++n_wave; n_task += plan.ntask;
         }
+        if (rank == 0 && threadIdx.x == 0) atomicAdd(g.nrec, (unsigned long long)st.seq);
 
         // ---- next chain for this group ----
         if (g.ngroups >= g.nchain) break;           // every chain had its own group
@@ -833,8 +918,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
         chain = *((volatile int32_t*)(g.group_chain + group * 2 + chain_pub));
         chain_pub ^= 1;
     }
-    if (KL2 && g.dbg && lane == 0 && warp < 2) g.dbg[8 + 4 * blockIdx.x + warp] = t_chain;
-    if (KL2 && g.dbg && lane == 0 && warp == 0) { g.dbg[8 + 4 * blockIdx.x + 2] = n_rows; g.dbg[8 + 4 * blockIdx.x + 3] = t_wait; }
+    if (KL2 && g.dbg && lane == 0 && (warp == 0 || warp == GW_CHAIN_WARP0)) g.dbg[8 + 4 * blockIdx.x + (warp == 0 ? 1 : 0)] = t_chain;
+    if (KL2 && g.dbg && lane == 0 && warp == GW_CHAIN_WARP0) { g.dbg[8 + 4 * blockIdx.x + 2] = n_rows; g.dbg[8 + 4 * blockIdx.x + 3] = t_wait; }
     if (g.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
         g.dbg[0] = t_plan; g.dbg[1] = t_eval; g.dbg[2] = t_bar; g.dbg[3] = t_dec; g.dbg[4] = n_wave; g.dbg[5] = n_task; g.dbg[6] = t_e1; g.dbg[7] = t_e2;
     }
@@ -844,7 +929,7 @@ inline size_t gw_smem_bytes(bool kl2) {
     const size_t plan = (sizeof(GwPlan) + 15) & ~(size_t)15;
     if (!kl2) return plan + GW_WARPS * sizeof(WarpScratch);
     return plan + GW_WARPS * sizeof(GwKl2Warp) + sizeof(float) * GW_RING_STAGES * GW_STAGE_FLOATS
-           + sizeof(uint64_t) * GW_RING_STAGES + sizeof(long long) * 2 * GW_WARPS;
+           + sizeof(uint64_t) * GW_RING_STAGES + sizeof(long long) * 2 * GW_CHAIN_WARPS;
 }
 
 inline cudaError_t gw_configure() {

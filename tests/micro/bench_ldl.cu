@@ -34,6 +34,27 @@ __global__ void __launch_bounds__(384, 1) k(const double* rec, int ntask, double
     if (lane == 0) { cyc[warp * 4 + 0] = t_stage; cyc[warp * 4 + 1] = t_form; cyc[warp * 4 + 2] = t_ldl; cyc[warp * 4 + 3] = t_tot; }
 }
 
+struct KScr { LdlScratch w; union { double rec[REC]; double Lsm[(D39 * (D39 - 1)) / 2 + 3]; }; double pinv[VS]; double dS[VS], dP[VS]; };
+__global__ void __launch_bounds__(384, 1) k2(const double* rec, int ntask, double* out, long long* cyc) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    KScr* ks = reinterpret_cast<KScr*>(sm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    KScr& k = ks[warp];
+    long long t_tot = 0, t_inv = 0;
+    for (int it = 0; it < ntask; ++it) {
+        const RecSrc X{rec + (size_t)((it * 12 + warp) % 64) * REC};
+        const long long c0 = clock64();
+        kl2_side_one(X, k, k.dS, k.dP, lane);
+        const long long c1 = clock64();
+        double ga, gb;
+        inv_diag<D39>(k.Lsm, k.pinv, lane, ga, gb);
+        const long long c2 = clock64();
+        if (lane == 0) out[warp * ntask + it] = k.dP[3] + ga + gb;
+        t_tot += c1 - c0; t_inv += c2 - c1;
+    }
+    if (lane == 0) { cyc[warp * 4 + 0] = t_tot; cyc[warp * 4 + 1] = t_inv; }
+}
+
 int main() {
     const int NREC = 64;
     std::vector<double> h((size_t)NREC * REC, 0.0);
@@ -60,6 +81,15 @@ int main() {
         double o; cudaMemcpy(&o, out, 8, cudaMemcpyDeviceToHost);
         printf("%2d warps: cycles/task stage %6.0f form %6.0f ldl %6.0f total %6.0f   (logdet %.6f)\n", nw,
                hc[0] / (double)ntask, hc[1] / (double)ntask, hc[2] / (double)ntask, hc[3] / (double)ntask, o);
+    }
+    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(12 * sizeof(KScr)));
+    for (int nw : {1, 4, 12}) {
+        const int ntask = 32;
+        for (int rep = 0; rep < 2; ++rep) k2<<<1, nw * 32, 12 * sizeof(KScr)>>>(d, ntask, out, cyc);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+        long long hc[48]; cudaMemcpy(hc, cyc, sizeof(hc), cudaMemcpyDeviceToHost);
+        printf("%2d warps: KL2 side cycles/task total %6.0f   (inv_diag alone %6.0f)\n", nw, hc[0] / (double)ntask, hc[1] / (double)ntask);
     }
     return 0;
 }
