@@ -159,6 +159,7 @@ struct ClDev {
     spkdiar_merge* out; int64_t cap;
     long long* nmerge;           // merges performed
     double* final_min;           // the minimum that stopped the loop
+    unsigned long long* dbg;     // optional phase cycle counters of CTA 0
 };
 
 __device__ __forceinline__ void cl_grid_barrier(unsigned long long* ctr, unsigned long long& target) {
@@ -180,12 +181,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
     double* merged = reinterpret_cast<double*>(cl_smem + CL_WARPS * sizeof(WarpScratch));
     ClBest* wbest = reinterpret_cast<ClBest*>(merged + REC);
     double* shd = reinterpret_cast<double*>(wbest + CL_WARPS);      // [0] ld_ab
-    uint32_t* abits = reinterpret_cast<uint32_t*>(shd + 2);
+    int* wbusy = reinterpret_cast<int*>(shd + 2);                   // [CL_WARPS] warp has a pair in round 0
+    uint32_t* abits = reinterpret_cast<uint32_t*>(wbusy + CL_WARPS);
     __shared__ ClBest gbest;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n = g.n;
-    const int64_t gwarp = (int64_t)blockIdx.x * CL_WARPS + warp;
+    // warp numbering interleaves the CTAs: with fewer rows than warps every SM gets some, and every CTA
+    // keeps idle warps (one of them computes ln|S_ab| during the rescoring)
+    const int64_t gwarp = (int64_t)warp * gridDim.x + blockIdx.x;
     const int64_t nwarps = (int64_t)gridDim.x * CL_WARPS;
     const int nwords = (int)((n + 31) / 32);
     for (int wd = threadIdx.x; wd < nwords; wd += CL_THREADS) {
@@ -198,16 +202,26 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
     long long nm = 0;
     double det_max = 0.0, det_min = CL_MAXINT_D;           // spk-clustering.py:418-419
 
+    long long t_scan = 0, t_b1 = 0, t_pick = 0, t_score = 0, t_b2 = 0;
     for (;;) {
+        const long long c0 = clock64();
         // ---------- SCAN: exact argmin over the alive part of the matrix ----------
         ClBest mine{d_inf(), INT64_MAX};
         for (int64_t r = gwarp; r < n; r += nwarps) {
             if (!((abits[r >> 5] >> (r & 31)) & 1u)) continue;
             const double* row = g.M + r * n;
-            for (int64_t c0 = 0; c0 < n; c0 += 32) {
-                const uint32_t word = abits[c0 >> 5];
-                const int64_t c = c0 + lane;
-                if ((word >> lane) & 1u) cl_take(mine, __ldcg(row + c), r * n + c);
+            for (int64_t c0 = 0; c0 < n; c0 += 32 * 8) {       // eight independent loads in flight per lane
+                double v[8];
+                bool ok[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t c = c0 + 32 * u + lane;
+                    ok[u] = c < n && ((abits[c >> 5] >> (c & 31)) & 1u);
+                    v[u] = ok[u] ? __ldcg(row + c) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (ok[u]) cl_take(mine, v[u], r * n + c0 + 32 * u + lane);
             }
         }
         mine = cl_warp_best(mine);
@@ -218,7 +232,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
             for (int w = 1; w < CL_WARPS; ++w) cl_take(b, wbest[w].v, wbest[w].idx);
             g.slots[(nm & 1) * gridDim.x + blockIdx.x] = b;
         }
+        const long long c1 = clock64();
         cl_grid_barrier(g.bar, bar_target);
+        const long long c2 = clock64();
         if (warp == 0) {
             ClBest b{d_inf(), INT64_MAX};
             const ClBest* sl = g.slots + (nm & 1) * gridDim.x;
@@ -238,6 +254,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
         const bool go = (mind <= g.threshold) || (g.max_spk > 0 && nalive > (int64_t)g.max_spk);
         if (!go || a == b) {
             if (blockIdx.x == 0 && threadIdx.x == 0) {
+                if (g.dbg) { g.dbg[0] = t_scan; g.dbg[1] = t_b1; g.dbg[2] = t_pick; g.dbg[3] = t_score; g.dbg[4] = t_b2; g.dbg[5] = nm; }
                 *g.nmerge = nm;
                 *g.final_min = mind;
                 g.stat[2] = (unsigned long long)__double_as_longlong(det_max);
@@ -252,24 +269,33 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
             g.out[nm] = mr;
         }
         // ---------- MERGE + RESCORE ----------
+        const long long c3 = clock64();
         for (int q = threadIdx.x; q < REC; q += CL_THREADS)
             merged[q] = __ldcg(g.rec + a * REC + q) + __ldcg(g.rec + b * REC + q);
         if (threadIdx.x == 0) abits[b >> 5] &= ~(1u << (b & 31));
         __syncthreads();
         const SmemSrc X{merged};
-        // Round 0: warp 0 of every CTA computes ln|S_ab| (redundantly across CTAs) while the
-        // other warps already factorise their first pooled matrix; one __syncthreads later
-        // everybody knows ln|S_ab|.  One call site of the factorisation for all of it.
+        // ln|S_ab| is needed by every pair of the rescoring.  Every CTA computes it itself (no
+        // broadcast): by a warp that has no pair in the first round if there is one (the usual
+        // case: fewer alive clusters than warps), else by warp 0 ahead of its own pairs - while
+        // the other warps already factorise their first pooled matrix.  One __syncthreads later
+        // everybody knows it.
         auto next_k = [&](int64_t from) {
             while (from < n && (from == a || !((abits[from >> 5] >> (from & 31)) & 1u))) from += nwarps;
             return from;
         };
         int64_t k = next_k(gwarp);
+        if (lane == 0) wbusy[warp] = k < n ? 1 : 0;
+        __syncthreads();
+        int ldw = 0;
+#pragma unroll
+        for (int w = CL_WARPS - 1; w >= 0; --w) if (!wbusy[w]) ldw = w;
+        const bool spare = !wbusy[ldw];          // the ld_ab warp has nothing else to do in round 0
         const double N1 = merged[L39::CNT];
         double ld_ab = 0.0;
         for (int round = 0;; ++round) {
             bool has; int term; int64_t kk;
-            if (round == 0 && warp == 0) { has = true; term = 0; kk = a; }
+            if (round == 0 && warp == ldw) { has = true; term = 0; kk = a; }
             else { has = k < n; term = 2; kk = has ? k : a; if (has) k = next_k(k + nwarps); }
             if (!has && round > 0) break;
             double t = 0.0;
@@ -278,9 +304,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
                 t = logdet_term(term, g.metric, X, Y, ws[warp], lane);
             }
             if (round == 0) {
-                if (warp == 0 && lane == 0) shd[0] = t;
+                if (warp == ldw && lane == 0) shd[0] = t;
                 __syncthreads();
                 ld_ab = shd[0];
+                (void)spare;
             }
             if (has && term == 2 && lane == 0) {
                 const double N2 = __ldcg(g.rec + kk * REC + L39::CNT);
@@ -291,7 +318,9 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
                 if (g.variant == 1) { g.M[kk * n + a] = d; cl_track(d, g.stat); }   // and column a
             }
         }
+        const long long c4 = clock64();
         cl_grid_barrier(g.bar, bar_target);
+        t_scan += c1 - c0; t_b1 += c2 - c1; t_pick += c3 - c2; t_score += c4 - c3; t_b2 += clock64() - c4;
         // ---------- commit (CTA 0): the merged record replaces a's ----------
         if (blockIdx.x == 0) {
             for (int q = threadIdx.x; q < REC; q += CL_THREADS) g.rec[a * REC + q] = merged[q];
@@ -320,6 +349,7 @@ __global__ void cl_alive_max(const double* __restrict__ M, const uint8_t* __rest
 
 inline size_t cl_smem_bytes(int64_t n) {
     return CL_WARPS * sizeof(WarpScratch) + REC * sizeof(double) + CL_WARPS * sizeof(ClBest) + 2 * sizeof(double)
+           + CL_WARPS * sizeof(int)
            + (size_t)((n + 31) / 32) * sizeof(uint32_t) + 16;
 }
 
