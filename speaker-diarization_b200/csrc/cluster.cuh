@@ -36,7 +36,7 @@ struct spkdiar_clus {
 
 namespace spk {
 
-constexpr int CL_WARPS = 8;
+constexpr int CL_WARPS = 12;
 constexpr int CL_THREADS = CL_WARPS * 32;
 #define CL_MAXINT_D 9223372036854775807.0      /* float(sys.maxint) == 2^63 */
 
@@ -153,6 +153,12 @@ struct ClDev {
     double* rec; double* ld; double* M; uint8_t* alive_out;
     int64_t n;
     int metric; double lambda; double threshold; int max_spk; int variant;
+    double* rowmin_v;            // [n] minimum of row r over the alive columns ...
+    int32_t* rowmin_c;           // [n] ... and its (first) column, -1: none
+    int32_t* repoch;             // [n] iteration whose flagged list holds row r
+    int32_t* flist;              // [2][n] flagged rows of the even / odd iterations (-(a+1): the merged row)
+    int32_t* fcount;             // [2]
+    ClBest* slotsB;              // [grid] per-CTA minimum of the row rewritten by the last rescoring
     ClBest* slots;               // [grid] per-CTA candidates, double-buffered by merge parity: [2][grid]
     unsigned long long* bar;
     unsigned long long* stat;    // [0]=max [1]=min (ordered keys) over finite distances; [2]=max_det [3]=min_det
@@ -205,23 +211,69 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
     long long t_scan = 0, t_b1 = 0, t_pick = 0, t_score = 0, t_b2 = 0;
     for (;;) {
         const long long c0 = clock64();
-        // ---------- SCAN: exact argmin over the alive part of the matrix ----------
+        // ---------- ARGMIN over the alive part of the matrix, from the row-minimum cache ----------
+        // rowmin[r] = first minimum of row r over the alive columns (ndarray.argmin order: NaN first,
+        // then value, then column).  A merge rewrites row a, kills column b and - variant 1 - rewrites
+        // column a.  Row a and every row whose cached minimum is no longer trustworthy are put on the
+        // FLAGGED LIST of the next iteration (epoch-stamped, so nobody has to clear flags); all other
+        // rows just compare their cached minimum with the one new entry.  An iteration then costs
+        // one pass over the n cached minima (a row per LANE) plus a few CTA-wide row rescans instead
+        // of n^2 entries; row a itself is rebuilt from the per-CTA minima of the rescoring.
+        const int par = (int)(nm & 1);
+        if (blockIdx.x == 0 && threadIdx.x == 0) g.fcount[par ^ 1] = 0;         // list of the next iteration
         ClBest mine{d_inf(), INT64_MAX};
-        for (int64_t r = gwarp; r < n; r += nwarps) {
-            if (!((abits[r >> 5] >> (r & 31)) & 1u)) continue;
-            const double* row = g.M + r * n;
-            for (int64_t c0 = 0; c0 < n; c0 += 32 * 8) {       // eight independent loads in flight per lane
-                double v[8];
-                bool ok[8];
+        {
+            const int nfl = __ldcg(g.fcount + par);
+            const int32_t* fl = g.flist + (int64_t)par * n;
+            for (int li = blockIdx.x; li < nfl; li += gridDim.x) {              // one flagged row per CTA at a time
+                const int32_t code = __ldcg(fl + li);
+                const int64_t r = code < 0 ? -(int64_t)code - 1 : code;
+                ClBest rb{d_inf(), INT64_MAX};
+                if (code < 0) {
+                    // the merged row: its entries are the distances of the last rescoring (minimum per
+                    // CTA in slotsB) and the diagonal
+                    for (int t = threadIdx.x; t <= (int)gridDim.x; t += CL_THREADS) {
+                        if (t < (int)gridDim.x) {
+                            const long long c = __ldcg((const long long*)&g.slotsB[t].idx);
+                            if (c != INT64_MAX) cl_take(rb, __ldcg(&g.slotsB[t].v), c);
+                        } else {
+                            cl_take(rb, __ldcg(g.M + r * n + r), r);
+                        }
+                    }
+                } else {
+                    const double* row = g.M + r * n;
+                    for (int64_t c0 = 0; c0 < n; c0 += CL_THREADS * 4) {        // four independent loads per thread
+                        double v[4];
+                        bool ok[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int64_t c = c0 + 32 * u + lane;
-                    ok[u] = c < n && ((abits[c >> 5] >> (c & 31)) & 1u);
-                    v[u] = ok[u] ? __ldcg(row + c) : 0.0;
+                        for (int u = 0; u < 4; ++u) {
+                            const int64_t c = c0 + CL_THREADS * u + threadIdx.x;
+                            ok[u] = c < n && ((abits[c >> 5] >> (c & 31)) & 1u);
+                            v[u] = ok[u] ? __ldcg(row + c) : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (ok[u]) cl_take(rb, v[u], c0 + CL_THREADS * u + threadIdx.x);
+                    }
                 }
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (ok[u]) cl_take(mine, v[u], r * n + c0 + 32 * u + lane);
+                rb = cl_warp_best(rb);
+                if (lane == 0) wbest[warp] = rb;
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    ClBest bb = wbest[0];
+                    for (int w = 1; w < CL_WARPS; ++w) cl_take(bb, wbest[w].v, wbest[w].idx);
+                    g.rowmin_v[r] = bb.v; g.rowmin_c[r] = bb.idx == INT64_MAX ? -1 : (int32_t)bb.idx;
+                    if (bb.idx != INT64_MAX) cl_take(mine, bb.v, r * n + bb.idx);
+                }
+                __syncthreads();
+            }
+            // the cached minima of all other alive rows, one row per lane
+            const int32_t epoch = (int32_t)nm;
+            for (int64_t r = gwarp * 32 + lane; r < n; r += nwarps * 32) {
+                if (!((abits[r >> 5] >> (r & 31)) & 1u)) continue;
+                if (__ldcg(g.repoch + r) == epoch) continue;                    // on the flagged list: its CTA has it
+                const int32_t rc = __ldcg(g.rowmin_c + r);
+                if (rc >= 0) cl_take(mine, __ldcg(g.rowmin_v + r), r * n + rc);
             }
         }
         mine = cl_warp_best(mine);
@@ -280,24 +332,53 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
         // case: fewer alive clusters than warps), else by warp 0 ahead of its own pairs - while
         // the other warps already factorise their first pooled matrix.  One __syncthreads later
         // everybody knows it.
-        auto next_k = [&](int64_t from) {
-            while (from < n && (from == a || !((abits[from >> 5] >> (from & 31)) & 1u))) from += nwarps;
-            return from;
+        // Pairs are dealt to the warps by ORDINAL among the alive clusters (a dense numbering: no warp
+        // gets two pairs while another has none because of where the dead indices happen to lie).
+        // select(o) = index of the o-th alive cluster: lanes count the bits of their share of the
+        // mask words, a warp scan finds the lane that holds the target, that lane walks its words.
+        const int wpl = (nwords + 31) / 32;                       // mask words per lane
+        int mycnt = 0;
+        for (int w = lane * wpl; w < (lane + 1) * wpl && w < nwords; ++w) mycnt += __popc(abits[w]);
+        int incl = mycnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total_alive = __shfl_sync(0xffffffffu, incl, 31);
+        auto select = [&](int64_t o) -> int64_t {                  // warp-uniform o; n when o >= #alive
+            if (o >= total_alive) return n;
+            const int excl = incl - mycnt;
+            const bool mine = o >= excl && o < incl;
+            int64_t found = 0;
+            if (mine) {
+                int rem = (int)o - excl;
+                for (int w = lane * wpl;; ++w) {
+                    const uint32_t word = abits[w];
+                    const int c = __popc(word);
+                    if (rem < c) { found = (int64_t)w * 32 + (__fns(word, 0, rem + 1)); break; }
+                    rem -= c;
+                }
+            }
+            const unsigned who = __ballot_sync(0xffffffffu, mine);
+            return __shfl_sync(0xffffffffu, found, __ffs(who) - 1);
         };
-        int64_t k = next_k(gwarp);
-        if (lane == 0) wbusy[warp] = k < n ? 1 : 0;
+        int64_t ord = gwarp;
+        int64_t k = select(ord);
+        if (lane == 0) wbusy[warp] = (k < n && k != a) ? 1 : 0;
         __syncthreads();
         int ldw = 0;
 #pragma unroll
         for (int w = CL_WARPS - 1; w >= 0; --w) if (!wbusy[w]) ldw = w;
-        const bool spare = !wbusy[ldw];          // the ld_ab warp has nothing else to do in round 0
         const double N1 = merged[L39::CNT];
         double ld_ab = 0.0;
+        ClBest rowa{d_inf(), INT64_MAX};             // lane 0: best (distance, k) this warp produced for row a
         for (int round = 0;; ++round) {
             bool has; int term; int64_t kk;
-            if (round == 0 && warp == ldw) { has = true; term = 0; kk = a; }
-            else { has = k < n; term = 2; kk = has ? k : a; if (has) k = next_k(k + nwarps); }
-            if (!has && round > 0) break;
+            if (round == 0 && warp == ldw && !wbusy[ldw]) { has = true; term = 0; kk = a; }       // a spare warp
+            else if (round == 0 && warp == ldw) { has = true; term = 0; kk = a; ord -= nwarps; }     // none spare: warp 0 first
+            else { has = k < n && k != a; term = 2; kk = has ? k : a; }
+            if (round > 0 && k >= n) break;
             double t = 0.0;
             if (has) {
                 const RecSrc Y{g.rec + kk * REC};
@@ -307,7 +388,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
                 if (warp == ldw && lane == 0) shd[0] = t;
                 __syncthreads();
                 ld_ab = shd[0];
-                (void)spare;
             }
             if (has && term == 2 && lane == 0) {
                 const double N2 = __ldcg(g.rec + kk * REC + L39::CNT);
@@ -315,7 +395,40 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
                 const double d = g.metric == SPKDIAR_BIC ? bic_combine(N1, N2, ld_ab, ldk, t, g.lambda)
                                                          : glr_combine(N1, N2, ld_ab, ldk, t);
                 g.M[a * n + kk] = d;                                            // row a
-                if (g.variant == 1) { g.M[kk * n + a] = d; cl_track(d, g.stat); }   // and column a
+                cl_take(rowa, d, kk);                                            // minimum of the new row a
+                const int32_t cmin = __ldcg(g.rowmin_c + kk);
+                bool flag = false;
+                if (g.variant == 1) {
+                    g.M[kk * n + a] = d; cl_track(d, g.stat);                   // and column a
+                    const double vold = __ldcg(g.rowmin_v + kk);
+                    if (cmin == (int32_t)b) flag = true;
+                    else if (cmin == (int32_t)a) {
+                        // the row's minimum sat in the rewritten column: it stays there unless it got worse
+                        if (cl_before(vold, a, d, a)) flag = true; else g.rowmin_v[kk] = d;
+                    } else if (cmin < 0 || cl_before(d, a, vold, cmin)) { g.rowmin_v[kk] = d; g.rowmin_c[kk] = (int32_t)a; }
+                } else if (cmin == (int32_t)b) {
+                    flag = true;                                                // column a keeps its stale entries (Q5)
+                }
+                if (flag) {
+                    g.repoch[kk] = (int32_t)(nm + 1);
+                    const int at = atomicAdd(g.fcount + (par ^ 1), 1);
+                    g.flist[(int64_t)(par ^ 1) * n + at] = (int32_t)kk;
+                }
+            }
+            ord += nwarps;
+            k = select(ord);
+        }
+        // per-CTA minimum of the new row a -> slotsB; row a goes on the flagged list as "merged row"
+        if (lane == 0) wbest[warp] = rowa;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ClBest bb = wbest[0];
+            for (int w = 1; w < CL_WARPS; ++w) cl_take(bb, wbest[w].v, wbest[w].idx);
+            g.slotsB[blockIdx.x] = bb;
+            if (blockIdx.x == 0) {
+                g.repoch[a] = (int32_t)(nm + 1);
+                const int at = atomicAdd(g.fcount + (par ^ 1), 1);
+                g.flist[(int64_t)(par ^ 1) * n + at] = -(int32_t)a - 1;
             }
         }
         const long long c4 = clock64();
