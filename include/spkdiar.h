@@ -196,12 +196,19 @@ int  spkdiar_cluster_create(spkdiar_feat* f, const int64_t* seg_a,
 int  spkdiar_cluster_run(spkdiar_clus* c, double threshold, int32_t max_spk,
                          int32_t variant, spkdiar_merge* out, int64_t cap,
                          int64_t* nmerges, double* stats4);
-/* row-sharded run for one very long recording (BASELINE config 5): this rank
- * owns the pair-matrix rows r with r % nranks == rank.  exchange() is called
- * once per merge with this rank's best candidate (16 bytes: fp64 distance,
- * int64 flat index) and must fill all[nranks] with every rank's candidate
- * (an all-gather; the host supplies it so that the library does not link
- * NCCL/MPI itself). */
+/* sharded run for one very long recording (BASELINE config 5), variant 1: the pair
+ * matrix is dealt out over nranks devices, pair (r, c) is scored and kept by rank
+ * (r + c) % nranks (every row of the matrix is spread evenly, so the rescoring of a
+ * merged row is balanced); cluster statistics are replicated, so every rank applies
+ * the same merges.  All ranks must have created the handle from the same segments.
+ * exchange() is called once per merge with this rank's best candidate (16 bytes:
+ * fp64 distance, int64 flat index r * nseg + c) and must fill all[nranks] with
+ * every rank's candidate (an all-gather; the host supplies it - torch.distributed,
+ * MPI, threads - so that the library does not link a communication library); it is
+ * called once more at the end with (max, min) of the distances for stats4.  The
+ * global minimum is taken with ndarray.argmin's order (NaN first, value, flat index),
+ * which makes the merge sequence identical to spkdiar_cluster_run's for any nranks.
+ * nranks == 1 needs no exchange function. */
 typedef int (*spkdiar_exchange_fn)(void* user, const void* mine16, void* all);
 int  spkdiar_cluster_run_sharded(spkdiar_clus* c, double threshold,
                                  int32_t max_spk, int32_t rank, int32_t nranks,

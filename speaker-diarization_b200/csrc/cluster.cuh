@@ -153,7 +153,8 @@ struct ClDev {
     double* rec; double* ld; double* M; uint8_t* alive_out;
     int64_t n;
     int metric; double lambda; double threshold; int max_spk; int variant;
-    double* rowmin_v;            // [n] minimum of row r over the alive columns ...
+    int32_t rank, nranks;        // pair (r, c) is scored and kept by rank (r + c) % nranks
+    double* rowmin_v;            // [n] minimum of row r over the alive (owned) columns ...
     int32_t* rowmin_c;           // [n] ... and its (first) column, -1: none
     int32_t* repoch;             // [n] iteration whose flagged list holds row r
     int32_t* flist;              // [2][n] flagged rows of the even / odd iterations (-(a+1): the merged row)
@@ -166,6 +167,11 @@ struct ClDev {
     long long* nmerge;           // merges performed
     double* final_min;           // the minimum that stopped the loop
     unsigned long long* dbg;     // optional phase cycle counters of CTA 0
+    // host-driven (sharded) run only: state that the persistent kernel keeps on chip
+    uint32_t* abits_g;           // [ceil(n/32)] alive mask
+    double* pend;                // [REC + 2] merged record, ln|S_ab|, index a (+1; 0 = nothing pending)
+    ClBest* local_best;          // this rank's candidate of the current iteration
+    unsigned int* ticket;        // last-CTA election of the argmin kernel
 };
 
 __device__ __forceinline__ void cl_grid_barrier(unsigned long long* ctr, unsigned long long& target) {
@@ -180,15 +186,243 @@ __device__ __forceinline__ void cl_grid_barrier(unsigned long long* ctr, unsigne
     __syncthreads();
 }
 
-// shared memory: alive bitmask [ceil(n/32)] words, merged record [REC], per-warp scratch
+// shared memory of the merge kernels: per-warp scratch, merged record [REC], small arrays, alive bitmask
+struct ClSmem {
+    WarpScratch* ws; double* merged; ClBest* wbest; double* shd; int* wbusy; uint32_t* abits;
+};
+__device__ __forceinline__ ClSmem cl_carve(unsigned char* base) {
+    ClSmem m;
+    m.ws = reinterpret_cast<WarpScratch*>(base);
+    m.merged = reinterpret_cast<double*>(base + CL_WARPS * sizeof(WarpScratch));
+    m.wbest = reinterpret_cast<ClBest*>(m.merged + REC);
+    m.shd = reinterpret_cast<double*>(m.wbest + CL_WARPS);          // [0] ld_ab
+    m.wbusy = reinterpret_cast<int*>(m.shd + 2);                    // [CL_WARPS] warp has a pair in round 0
+    m.abits = reinterpret_cast<uint32_t*>(m.wbusy + CL_WARPS);
+    return m;
+}
+__device__ __forceinline__ bool cl_own(const ClDev& g, int64_t r, int64_t c) {
+    return g.nranks == 1 || (int32_t)((r + c) % g.nranks) == g.rank;
+}
+
+// ---------- ARGMIN over the alive (owned) part of the matrix, from the row-minimum cache ----------
+// rowmin[r] = first minimum of row r over the alive columns (ndarray.argmin order: NaN first,
+// then value, then column).  A merge rewrites row a, kills column b and - variant 1 - rewrites
+// column a.  Row a and every row whose cached minimum is no longer trustworthy are put on the
+// FLAGGED LIST of the next iteration (epoch-stamped, so nobody has to clear flags); all other
+// rows just compare their cached minimum with the one new entry.  An iteration then costs
+// one pass over the n cached minima (a row per LANE) plus a few CTA-wide row rescans instead
+// of n^2 entries; row a itself is rebuilt from the per-CTA minima of the rescoring.
+// Returns this CTA's candidate in thread 0.
+__device__ __forceinline__ ClBest cl_phase_argmin(const ClDev& g, long long nm, const ClSmem& sm,
+                                                  int warp, int lane, int64_t gwarp, int64_t nwarps) {
+    const int64_t n = g.n;
+    const uint32_t* abits = sm.abits;
+    ClBest* wbest = sm.wbest;
+    const int par = (int)(nm & 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) g.fcount[par ^ 1] = 0;         // list of the next iteration
+    ClBest mine{d_inf(), INT64_MAX};
+    const int nfl = __ldcg(g.fcount + par);
+    const int32_t* fl = g.flist + (int64_t)par * n;
+    for (int li = blockIdx.x; li < nfl; li += gridDim.x) {                  // one flagged row per CTA at a time
+        const int32_t code = __ldcg(fl + li);
+        const int64_t r = code < 0 ? -(int64_t)code - 1 : code;
+        ClBest rb{d_inf(), INT64_MAX};
+        if (code < 0) {
+            // the merged row: its entries are the distances of the last rescoring (minimum per
+            // CTA in slotsB) and the diagonal
+            for (int t = threadIdx.x; t <= (int)gridDim.x; t += CL_THREADS) {
+                if (t < (int)gridDim.x) {
+                    const long long c = __ldcg((const long long*)&g.slotsB[t].idx);
+                    if (c != INT64_MAX) cl_take(rb, __ldcg(&g.slotsB[t].v), c);
+                } else if (cl_own(g, r, r)) {
+                    cl_take(rb, __ldcg(g.M + r * n + r), r);
+                }
+            }
+        } else {
+            const double* row = g.M + r * n;
+            for (int64_t c0 = 0; c0 < n; c0 += CL_THREADS * 4) {            // four independent loads per thread
+                double v[4];
+                bool ok[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t c = c0 + CL_THREADS * u + threadIdx.x;
+                    ok[u] = c < n && ((abits[c >> 5] >> (c & 31)) & 1u) && cl_own(g, r, c);
+                    v[u] = ok[u] ? __ldcg(row + c) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (ok[u]) cl_take(rb, v[u], c0 + CL_THREADS * u + threadIdx.x);
+            }
+        }
+        rb = cl_warp_best(rb);
+        if (lane == 0) wbest[warp] = rb;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ClBest bb = wbest[0];
+            for (int w = 1; w < CL_WARPS; ++w) cl_take(bb, wbest[w].v, wbest[w].idx);
+            g.rowmin_v[r] = bb.v; g.rowmin_c[r] = bb.idx == INT64_MAX ? -1 : (int32_t)bb.idx;
+            if (bb.idx != INT64_MAX) cl_take(mine, bb.v, r * n + bb.idx);
+        }
+        __syncthreads();
+    }
+    // the cached minima of all other alive rows, one row per lane
+    const int32_t epoch = (int32_t)nm;
+    for (int64_t r = gwarp * 32 + lane; r < n; r += nwarps * 32) {
+        if (!((abits[r >> 5] >> (r & 31)) & 1u)) continue;
+        if (__ldcg(g.repoch + r) == epoch) continue;                        // on the flagged list: its CTA has it
+        const int32_t rc = __ldcg(g.rowmin_c + r);
+        if (rc >= 0) cl_take(mine, __ldcg(g.rowmin_v + r), r * n + rc);
+    }
+    mine = cl_warp_best(mine);
+    if (lane == 0) wbest[warp] = mine;
+    __syncthreads();
+    ClBest out{d_inf(), INT64_MAX};
+    if (threadIdx.x == 0) {
+        out = wbest[0];
+        for (int w = 1; w < CL_WARPS; ++w) cl_take(out, wbest[w].v, wbest[w].idx);
+    }
+    __syncthreads();
+    return out;
+}
+
+// ---------- MERGE + RESCORE: clusters a and b (a < b) become a ----------
+// sm.merged must hold rec[a] + rec[b] and bit b of sm.abits must be cleared (and a
+// __syncthreads passed).  Scores the merged cluster against every alive cluster k whose
+// pair (a, k) this rank owns, writes row a (and column a in variant 1), maintains the
+// row-minimum cache and the flagged list of iteration nm + 1.  Returns ln|S_ab|.
+__device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, int64_t a, int64_t b, const ClSmem& sm,
+                                                 int warp, int lane, int64_t gwarp, int64_t nwarps) {
+    const int64_t n = g.n;
+    const uint32_t* abits = sm.abits;
+    const int nwords = (int)((n + 31) / 32);
+    const int par = (int)(nm & 1);
+    const SmemSrc X{sm.merged};
+    // ln|S_ab| is needed by every pair of the rescoring.  Every CTA computes it itself (no
+    // broadcast): by a warp that has no pair in the first round if there is one (the usual
+    // case: fewer alive clusters than warps), else by warp 0 ahead of its own pairs - while
+    // the other warps already factorise their first pooled matrix.  One __syncthreads later
+    // everybody knows it.
+    // Pairs are dealt to the warps by ORDINAL among the alive clusters (a dense numbering: no warp
+    // gets two pairs while another has none because of where the dead indices happen to lie).
+    // select(o) = index of the o-th alive cluster: lanes count the bits of their share of the
+    // mask words, a warp scan finds the lane that holds the target, that lane walks its words.
+    const int wpl = (nwords + 31) / 32;                       // mask words per lane
+    int mycnt = 0;
+    for (int w = lane * wpl; w < (lane + 1) * wpl && w < nwords; ++w) mycnt += __popc(abits[w]);
+    int incl = mycnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total_alive = __shfl_sync(0xffffffffu, incl, 31);
+    auto select = [&](int64_t o) -> int64_t {                  // warp-uniform o; n when o >= #alive
+        if (o >= total_alive) return n;
+        const int excl = incl - mycnt;
+        const bool mine = o >= excl && o < incl;
+        int64_t found = 0;
+        if (mine) {
+            int rem = (int)o - excl;
+            for (int w = lane * wpl;; ++w) {
+                const uint32_t word = abits[w];
+                const int c = __popc(word);
+                if (rem < c) { found = (int64_t)w * 32 + (__fns(word, 0, rem + 1)); break; }
+                rem -= c;
+            }
+        }
+        const unsigned who = __ballot_sync(0xffffffffu, mine);
+        return __shfl_sync(0xffffffffu, found, __ffs(who) - 1);
+    };
+    int64_t ord = gwarp;
+    int64_t k = select(ord);
+    auto mine_pair = [&](int64_t kk) { return kk < n && kk != a && cl_own(g, a, kk); };
+    if (lane == 0) sm.wbusy[warp] = mine_pair(k) ? 1 : 0;
+    __syncthreads();
+    int ldw = 0;
+#pragma unroll
+    for (int w = CL_WARPS - 1; w >= 0; --w) if (!sm.wbusy[w]) ldw = w;
+    const double N1 = sm.merged[L39::CNT];
+    double ld_ab = 0.0;
+    ClBest rowa{d_inf(), INT64_MAX};             // lane 0: best (distance, k) this warp produced for row a
+    for (int round = 0;; ++round) {
+        bool has; int term; int64_t kk;
+        if (round == 0 && warp == ldw && !sm.wbusy[ldw]) { has = true; term = 0; kk = a; }       // a spare warp
+        else if (round == 0 && warp == ldw) { has = true; term = 0; kk = a; ord -= nwarps; }     // none spare: warp 0 first
+        else { has = mine_pair(k); term = 2; kk = has ? k : a; }
+        if (round > 0 && k >= n) break;
+        double t = 0.0;
+        if (has) {
+            const RecSrc Y{g.rec + kk * REC};
+            t = logdet_term(term, g.metric, X, Y, sm.ws[warp], lane);
+        }
+        if (round == 0) {
+            if (warp == ldw && lane == 0) sm.shd[0] = t;
+            __syncthreads();
+            ld_ab = sm.shd[0];
+        }
+        if (has && term == 2 && lane == 0) {
+            const double N2 = __ldcg(g.rec + kk * REC + L39::CNT);
+            const double ldk = __ldcg(g.ld + kk);
+            const double d = g.metric == SPKDIAR_BIC ? bic_combine(N1, N2, ld_ab, ldk, t, g.lambda)
+                                                     : glr_combine(N1, N2, ld_ab, ldk, t);
+            g.M[a * n + kk] = d;                                            // row a
+            cl_take(rowa, d, kk);                                            // minimum of the new row a
+            const int32_t cmin = __ldcg(g.rowmin_c + kk);
+            bool flag = false;
+            if (g.variant == 1) {
+                g.M[kk * n + a] = d; cl_track(d, g.stat);                   // and column a
+                const double vold = __ldcg(g.rowmin_v + kk);
+                if (cmin == (int32_t)b) flag = true;
+                else if (cmin == (int32_t)a) {
+                    // the row's minimum sat in the rewritten column: it stays there unless it got worse
+                    if (cl_before(vold, a, d, a)) flag = true; else g.rowmin_v[kk] = d;
+                } else if (cmin < 0 || cl_before(d, a, vold, cmin)) { g.rowmin_v[kk] = d; g.rowmin_c[kk] = (int32_t)a; }
+            } else if (cmin == (int32_t)b) {
+                flag = true;                                                // column a keeps its stale entries (Q5)
+            }
+            if (flag) {
+                g.repoch[kk] = (int32_t)(nm + 1);
+                const int at = atomicAdd(g.fcount + (par ^ 1), 1);
+                g.flist[(int64_t)(par ^ 1) * n + at] = (int32_t)kk;
+            }
+        }
+        ord += nwarps;
+        k = select(ord);
+    }
+    // A row whose pair with a belongs to ANOTHER rank still loses column b here: if its cached
+    // minimum sat there (or in the column a another rank rewrites - not this rank's entry, so the
+    // local row only loses it) it has to be rescanned.  One lane per row.
+    if (g.nranks > 1) {
+        for (int64_t r = gwarp * 32 + lane; r < n; r += nwarps * 32) {
+            if (!((abits[r >> 5] >> (r & 31)) & 1u) || r == a || cl_own(g, a, r)) continue;
+            const int32_t cmin = __ldcg(g.rowmin_c + r);
+            if (cmin == (int32_t)b) {
+                g.repoch[r] = (int32_t)(nm + 1);
+                const int at = atomicAdd(g.fcount + (par ^ 1), 1);
+                g.flist[(int64_t)(par ^ 1) * n + at] = (int32_t)r;
+            }
+        }
+    }
+    // per-CTA minimum of the new row a -> slotsB; row a goes on the flagged list as "merged row"
+    if (lane == 0) sm.wbest[warp] = rowa;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ClBest bb = sm.wbest[0];
+        for (int w = 1; w < CL_WARPS; ++w) cl_take(bb, sm.wbest[w].v, sm.wbest[w].idx);
+        g.slotsB[blockIdx.x] = bb;
+        if (blockIdx.x == 0) {
+            g.repoch[a] = (int32_t)(nm + 1);
+            const int at = atomicAdd(g.fcount + (par ^ 1), 1);
+            g.flist[(int64_t)(par ^ 1) * n + at] = -(int32_t)a - 1;
+        }
+    }
+    return ld_ab;
+}
+
+// the merge loop as ONE persistent cooperative kernel (single GPU)
 __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
     extern __shared__ __align__(16) unsigned char cl_smem[];
-    WarpScratch* ws = reinterpret_cast<WarpScratch*>(cl_smem);
-    double* merged = reinterpret_cast<double*>(cl_smem + CL_WARPS * sizeof(WarpScratch));
-    ClBest* wbest = reinterpret_cast<ClBest*>(merged + REC);
-    double* shd = reinterpret_cast<double*>(wbest + CL_WARPS);      // [0] ld_ab
-    int* wbusy = reinterpret_cast<int*>(shd + 2);                   // [CL_WARPS] warp has a pair in round 0
-    uint32_t* abits = reinterpret_cast<uint32_t*>(wbusy + CL_WARPS);
+    const ClSmem sm = cl_carve(cl_smem);
     __shared__ ClBest gbest;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -200,7 +434,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
     const int nwords = (int)((n + 31) / 32);
     for (int wd = threadIdx.x; wd < nwords; wd += CL_THREADS) {
         const int64_t lo = (int64_t)wd * 32;
-        abits[wd] = (n - lo >= 32) ? 0xffffffffu : ((1u << (int)(n - lo)) - 1u);
+        sm.abits[wd] = (n - lo >= 32) ? 0xffffffffu : ((1u << (int)(n - lo)) - 1u);
     }
     __syncthreads();
     unsigned long long bar_target = 0;
@@ -211,79 +445,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
     long long t_scan = 0, t_b1 = 0, t_pick = 0, t_score = 0, t_b2 = 0;
     for (;;) {
         const long long c0 = clock64();
-        // ---------- ARGMIN over the alive part of the matrix, from the row-minimum cache ----------
-        // rowmin[r] = first minimum of row r over the alive columns (ndarray.argmin order: NaN first,
-        // then value, then column).  A merge rewrites row a, kills column b and - variant 1 - rewrites
-        // column a.  Row a and every row whose cached minimum is no longer trustworthy are put on the
-        // FLAGGED LIST of the next iteration (epoch-stamped, so nobody has to clear flags); all other
-        // rows just compare their cached minimum with the one new entry.  An iteration then costs
-        // one pass over the n cached minima (a row per LANE) plus a few CTA-wide row rescans instead
-        // of n^2 entries; row a itself is rebuilt from the per-CTA minima of the rescoring.
-        const int par = (int)(nm & 1);
-        if (blockIdx.x == 0 && threadIdx.x == 0) g.fcount[par ^ 1] = 0;         // list of the next iteration
-        ClBest mine{d_inf(), INT64_MAX};
-        {
-            const int nfl = __ldcg(g.fcount + par);
-            const int32_t* fl = g.flist + (int64_t)par * n;
-            for (int li = blockIdx.x; li < nfl; li += gridDim.x) {              // one flagged row per CTA at a time
-                const int32_t code = __ldcg(fl + li);
-                const int64_t r = code < 0 ? -(int64_t)code - 1 : code;
-                ClBest rb{d_inf(), INT64_MAX};
-                if (code < 0) {
-                    // the merged row: its entries are the distances of the last rescoring (minimum per
-                    // CTA in slotsB) and the diagonal
-                    for (int t = threadIdx.x; t <= (int)gridDim.x; t += CL_THREADS) {
-                        if (t < (int)gridDim.x) {
-                            const long long c = __ldcg((const long long*)&g.slotsB[t].idx);
-                            if (c != INT64_MAX) cl_take(rb, __ldcg(&g.slotsB[t].v), c);
-                        } else {
-                            cl_take(rb, __ldcg(g.M + r * n + r), r);
-                        }
-                    }
-                } else {
-                    const double* row = g.M + r * n;
-                    for (int64_t c0 = 0; c0 < n; c0 += CL_THREADS * 4) {        // four independent loads per thread
-                        double v[4];
-                        bool ok[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int64_t c = c0 + CL_THREADS * u + threadIdx.x;
-                            ok[u] = c < n && ((abits[c >> 5] >> (c & 31)) & 1u);
-                            v[u] = ok[u] ? __ldcg(row + c) : 0.0;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (ok[u]) cl_take(rb, v[u], c0 + CL_THREADS * u + threadIdx.x);
-                    }
-                }
-                rb = cl_warp_best(rb);
-                if (lane == 0) wbest[warp] = rb;
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    ClBest bb = wbest[0];
-                    for (int w = 1; w < CL_WARPS; ++w) cl_take(bb, wbest[w].v, wbest[w].idx);
-                    g.rowmin_v[r] = bb.v; g.rowmin_c[r] = bb.idx == INT64_MAX ? -1 : (int32_t)bb.idx;
-                    if (bb.idx != INT64_MAX) cl_take(mine, bb.v, r * n + bb.idx);
-                }
-                __syncthreads();
-            }
-            // the cached minima of all other alive rows, one row per lane
-            const int32_t epoch = (int32_t)nm;
-            for (int64_t r = gwarp * 32 + lane; r < n; r += nwarps * 32) {
-                if (!((abits[r >> 5] >> (r & 31)) & 1u)) continue;
-                if (__ldcg(g.repoch + r) == epoch) continue;                    // on the flagged list: its CTA has it
-                const int32_t rc = __ldcg(g.rowmin_c + r);
-                if (rc >= 0) cl_take(mine, __ldcg(g.rowmin_v + r), r * n + rc);
-            }
-        }
-        mine = cl_warp_best(mine);
-        if (lane == 0) wbest[warp] = mine;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            ClBest b = wbest[0];
-            for (int w = 1; w < CL_WARPS; ++w) cl_take(b, wbest[w].v, wbest[w].idx);
-            g.slots[(nm & 1) * gridDim.x + blockIdx.x] = b;
-        }
+        const ClBest cta = cl_phase_argmin(g, nm, sm, warp, lane, gwarp, nwarps);
+        if (threadIdx.x == 0) g.slots[(nm & 1) * gridDim.x + blockIdx.x] = cta;
         const long long c1 = clock64();
         cl_grid_barrier(g.bar, bar_target);
         const long long c2 = clock64();
@@ -320,123 +483,18 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
             spkdiar_merge mr; mr.a = (int32_t)a; mr.b = (int32_t)b; mr.d = mind;
             g.out[nm] = mr;
         }
-        // ---------- MERGE + RESCORE ----------
         const long long c3 = clock64();
         for (int q = threadIdx.x; q < REC; q += CL_THREADS)
-            merged[q] = __ldcg(g.rec + a * REC + q) + __ldcg(g.rec + b * REC + q);
-        if (threadIdx.x == 0) abits[b >> 5] &= ~(1u << (b & 31));
+            sm.merged[q] = __ldcg(g.rec + a * REC + q) + __ldcg(g.rec + b * REC + q);
+        if (threadIdx.x == 0) sm.abits[b >> 5] &= ~(1u << (b & 31));
         __syncthreads();
-        const SmemSrc X{merged};
-        // ln|S_ab| is needed by every pair of the rescoring.  Every CTA computes it itself (no
-        // broadcast): by a warp that has no pair in the first round if there is one (the usual
-        // case: fewer alive clusters than warps), else by warp 0 ahead of its own pairs - while
-        // the other warps already factorise their first pooled matrix.  One __syncthreads later
-        // everybody knows it.
-        // Pairs are dealt to the warps by ORDINAL among the alive clusters (a dense numbering: no warp
-        // gets two pairs while another has none because of where the dead indices happen to lie).
-        // select(o) = index of the o-th alive cluster: lanes count the bits of their share of the
-        // mask words, a warp scan finds the lane that holds the target, that lane walks its words.
-        const int wpl = (nwords + 31) / 32;                       // mask words per lane
-        int mycnt = 0;
-        for (int w = lane * wpl; w < (lane + 1) * wpl && w < nwords; ++w) mycnt += __popc(abits[w]);
-        int incl = mycnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total_alive = __shfl_sync(0xffffffffu, incl, 31);
-        auto select = [&](int64_t o) -> int64_t {                  // warp-uniform o; n when o >= #alive
-            if (o >= total_alive) return n;
-            const int excl = incl - mycnt;
-            const bool mine = o >= excl && o < incl;
-            int64_t found = 0;
-            if (mine) {
-                int rem = (int)o - excl;
-                for (int w = lane * wpl;; ++w) {
-                    const uint32_t word = abits[w];
-                    const int c = __popc(word);
-                    if (rem < c) { found = (int64_t)w * 32 + (__fns(word, 0, rem + 1)); break; }
-                    rem -= c;
-                }
-            }
-            const unsigned who = __ballot_sync(0xffffffffu, mine);
-            return __shfl_sync(0xffffffffu, found, __ffs(who) - 1);
-        };
-        int64_t ord = gwarp;
-        int64_t k = select(ord);
-        if (lane == 0) wbusy[warp] = (k < n && k != a) ? 1 : 0;
-        __syncthreads();
-        int ldw = 0;
-#pragma unroll
-        for (int w = CL_WARPS - 1; w >= 0; --w) if (!wbusy[w]) ldw = w;
-        const double N1 = merged[L39::CNT];
-        double ld_ab = 0.0;
-        ClBest rowa{d_inf(), INT64_MAX};             // lane 0: best (distance, k) this warp produced for row a
-        for (int round = 0;; ++round) {
-            bool has; int term; int64_t kk;
-            if (round == 0 && warp == ldw && !wbusy[ldw]) { has = true; term = 0; kk = a; }       // a spare warp
-            else if (round == 0 && warp == ldw) { has = true; term = 0; kk = a; ord -= nwarps; }     // none spare: warp 0 first
-            else { has = k < n && k != a; term = 2; kk = has ? k : a; }
-            if (round > 0 && k >= n) break;
-            double t = 0.0;
-            if (has) {
-                const RecSrc Y{g.rec + kk * REC};
-                t = logdet_term(term, g.metric, X, Y, ws[warp], lane);
-            }
-            if (round == 0) {
-                if (warp == ldw && lane == 0) shd[0] = t;
-                __syncthreads();
-                ld_ab = shd[0];
-            }
-            if (has && term == 2 && lane == 0) {
-                const double N2 = __ldcg(g.rec + kk * REC + L39::CNT);
-                const double ldk = __ldcg(g.ld + kk);
-                const double d = g.metric == SPKDIAR_BIC ? bic_combine(N1, N2, ld_ab, ldk, t, g.lambda)
-                                                         : glr_combine(N1, N2, ld_ab, ldk, t);
-                g.M[a * n + kk] = d;                                            // row a
-                cl_take(rowa, d, kk);                                            // minimum of the new row a
-                const int32_t cmin = __ldcg(g.rowmin_c + kk);
-                bool flag = false;
-                if (g.variant == 1) {
-                    g.M[kk * n + a] = d; cl_track(d, g.stat);                   // and column a
-                    const double vold = __ldcg(g.rowmin_v + kk);
-                    if (cmin == (int32_t)b) flag = true;
-                    else if (cmin == (int32_t)a) {
-                        // the row's minimum sat in the rewritten column: it stays there unless it got worse
-                        if (cl_before(vold, a, d, a)) flag = true; else g.rowmin_v[kk] = d;
-                    } else if (cmin < 0 || cl_before(d, a, vold, cmin)) { g.rowmin_v[kk] = d; g.rowmin_c[kk] = (int32_t)a; }
-                } else if (cmin == (int32_t)b) {
-                    flag = true;                                                // column a keeps its stale entries (Q5)
-                }
-                if (flag) {
-                    g.repoch[kk] = (int32_t)(nm + 1);
-                    const int at = atomicAdd(g.fcount + (par ^ 1), 1);
-                    g.flist[(int64_t)(par ^ 1) * n + at] = (int32_t)kk;
-                }
-            }
-            ord += nwarps;
-            k = select(ord);
-        }
-        // per-CTA minimum of the new row a -> slotsB; row a goes on the flagged list as "merged row"
-        if (lane == 0) wbest[warp] = rowa;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            ClBest bb = wbest[0];
-            for (int w = 1; w < CL_WARPS; ++w) cl_take(bb, wbest[w].v, wbest[w].idx);
-            g.slotsB[blockIdx.x] = bb;
-            if (blockIdx.x == 0) {
-                g.repoch[a] = (int32_t)(nm + 1);
-                const int at = atomicAdd(g.fcount + (par ^ 1), 1);
-                g.flist[(int64_t)(par ^ 1) * n + at] = -(int32_t)a - 1;
-            }
-        }
+        const double ld_ab = cl_phase_apply(g, nm, a, b, sm, warp, lane, gwarp, nwarps);
         const long long c4 = clock64();
         cl_grid_barrier(g.bar, bar_target);
         t_scan += c1 - c0; t_b1 += c2 - c1; t_pick += c3 - c2; t_score += c4 - c3; t_b2 += clock64() - c4;
         // ---------- commit (CTA 0): the merged record replaces a's ----------
         if (blockIdx.x == 0) {
-            for (int q = threadIdx.x; q < REC; q += CL_THREADS) g.rec[a * REC + q] = merged[q];
+            for (int q = threadIdx.x; q < REC; q += CL_THREADS) g.rec[a * REC + q] = sm.merged[q];
             if (threadIdx.x == 0) g.ld[a] = ld_ab;
         }
         --nalive;
@@ -444,7 +502,99 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
     }
     if (blockIdx.x == 0) {
         __syncthreads();
-        for (int64_t i = threadIdx.x; i < n; i += CL_THREADS) g.alive_out[i] = (abits[i >> 5] >> (i & 31)) & 1u;
+        for (int64_t i = threadIdx.x; i < n; i += CL_THREADS) g.alive_out[i] = (sm.abits[i >> 5] >> (i & 31)) & 1u;
+    }
+}
+
+// ---- the same two phases as separate launches (row-sharded run: the host exchanges the ranks'
+// candidates between them) ----
+__global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_argmin(const ClDev g, long long nm) {
+    extern __shared__ __align__(16) unsigned char cl_smem[];
+    const ClSmem sm = cl_carve(cl_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gwarp = (int64_t)warp * gridDim.x + blockIdx.x;
+    const int64_t nwarps = (int64_t)gridDim.x * CL_WARPS;
+    const int nwords = (int)((g.n + 31) / 32);
+    for (int wd = threadIdx.x; wd < nwords; wd += CL_THREADS) sm.abits[wd] = g.abits_g[wd];
+    // commit the merge of the previous iteration (nobody reads records in this kernel)
+    if (blockIdx.x == 0) {
+        const int64_t pa = (int64_t)g.pend[REC + 1] - 1;
+        if (pa >= 0) {
+            for (int q = threadIdx.x; q < REC; q += CL_THREADS) g.rec[pa * REC + q] = g.pend[q];
+            if (threadIdx.x == 0) g.ld[pa] = g.pend[REC];
+        }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) g.pend[REC + 1] = 0.0;
+    const ClBest cta = cl_phase_argmin(g, nm, sm, warp, lane, gwarp, nwarps);
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        g.slots[blockIdx.x] = cta;
+        __threadfence();
+        last = atomicAdd(g.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && warp == 0) {
+        __threadfence();
+        ClBest b{d_inf(), INT64_MAX};
+        for (int s = lane; s < (int)gridDim.x; s += 32) {
+            const double v = __ldcg(&g.slots[s].v);
+            const long long i = __ldcg((const long long*)&g.slots[s].idx);
+            cl_take(b, v, i);
+        }
+        b = cl_warp_best(b);
+        if (lane == 0) { *g.local_best = b; *g.ticket = 0u; }
+    }
+}
+
+__global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_apply(const ClDev g, long long nm, int64_t a, int64_t b) {
+    extern __shared__ __align__(16) unsigned char cl_smem[];
+    const ClSmem sm = cl_carve(cl_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gwarp = (int64_t)warp * gridDim.x + blockIdx.x;
+    const int64_t nwarps = (int64_t)gridDim.x * CL_WARPS;
+    const int nwords = (int)((g.n + 31) / 32);
+    for (int wd = threadIdx.x; wd < nwords; wd += CL_THREADS) {
+        uint32_t w = g.abits_g[wd];
+        if (wd == (int)(b >> 5)) w &= ~(1u << (b & 31));            // whoever reads it before CTA 0 stores it
+        sm.abits[wd] = w;
+    }
+    for (int q = threadIdx.x; q < REC; q += CL_THREADS)
+        sm.merged[q] = __ldcg(g.rec + a * REC + q) + __ldcg(g.rec + b * REC + q);
+    __syncthreads();
+    const double ld_ab = cl_phase_apply(g, nm, a, b, sm, warp, lane, gwarp, nwarps);
+    if (blockIdx.x == 0) {
+        // the merged record is committed by the next argmin launch (other CTAs still read rec[a] here)
+        for (int q = threadIdx.x; q < REC; q += CL_THREADS) g.pend[q] = sm.merged[q];
+        if (threadIdx.x == 0) {
+            g.pend[REC] = ld_ab;
+            g.pend[REC + 1] = (double)(a + 1);
+            atomicAnd(g.abits_g + (b >> 5), ~(1u << (b & 31)));
+        }
+    }
+}
+
+// initial fill of the pairs this rank owns (nranks > 1)
+__global__ void __launch_bounds__(SC_THREADS, 3)
+cl_fill_pairs_shard(const double* rec, const double* __restrict__ ld, int64_t n, int metric, double lambda,
+                    int rank, int nranks, double* __restrict__ M, unsigned long long* stat) {
+    extern __shared__ __align__(16) unsigned char sc_smem[];
+    WarpScratch* ws = reinterpret_cast<WarpScratch*>(sc_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // owned pairs of row i: j = i + 1 + ((rank - 2 i - 1) mod nranks) + t * nranks; rows are dealt to the warps
+    // cyclically, a row's owned pairs in turn
+    const int64_t gw = (int64_t)blockIdx.x * SC_WARPS + warp, nw = (int64_t)gridDim.x * SC_WARPS;
+    // linear index over (i, t): row i has cnt(i) = number of j > i with (i + j) % nranks == rank
+    for (int64_t i = 0; i < n - 1; ++i) {
+        int64_t j0 = i + 1 + ((((int64_t)rank - 2 * i - 1) % nranks) + nranks) % nranks;
+        // warps stride over the owned pairs of the row, offset by the row so that short rows do not
+        // always start at warp 0
+        for (int64_t t = (gw + nw - (i % nw)) % nw; j0 + t * nranks < n; t += nw) {
+            const int64_t j = j0 + t * nranks;
+            const RecSrc X{rec + i * REC}, Y{rec + j * REC};
+            const double d = cl_pair_distance(metric, lambda, X, Y, ld[i], ld[j], ws[warp], lane);
+            if (lane == 0) { M[i * n + j] = d; M[j * n + i] = d; cl_track(d, stat); }
+        }
     }
 }
 
@@ -468,6 +618,12 @@ inline size_t cl_smem_bytes(int64_t n) {
 
 inline cudaError_t cluster_configure() {
     cudaError_t e = cudaFuncSetAttribute(cl_merge_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(cl_shard_argmin, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(cl_shard_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(cl_fill_pairs_shard, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(cl_self_logdet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
     if (e != cudaSuccess) return e;

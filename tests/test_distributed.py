@@ -100,3 +100,96 @@ def test_two_gloo_ranks_equal_one_process(tmp_path):
             a = open(str(tmp_path / 'one' / (name + ext))).read()
             b = open(str(tmp_path / 'two' / (name + ext))).read()
             assert a == b and a.count('\n') >= 1
+
+
+# ---- sharded clustering: exchange + global pick over two gloo ranks ---------------------------
+
+def _sharded_cpu_loop(rank, world, exchange, frames, seg, threshold):
+    """The host logic of the sharded merge loop (spkdiar_cluster_run_sharded) with the oracle's
+    BIC as the distance: this rank keeps the pairs (r, c) with (r + c) % world == rank, proposes
+    its best one, the ranks exchange 16-byte candidates and apply the global minimum."""
+    import struct
+    import warnings
+    import numpy as np
+    from oracle import distances as OD
+    from spkdiar import sharded
+    warnings.simplefilter('ignore')
+    n = len(seg)
+    members = [[s] for s in seg]
+    alive = [True] * n
+
+    def feats(k):
+        return np.concatenate([frames[a:b] for a, b in members[k]])
+
+    def d(i, j):
+        return float(OD.bic_cl(feats(i), feats(j), 1.3))
+    M = {}
+    for i in range(n):
+        for j in range(i + 1, n):
+            if (i + j) % world == rank:
+                M[(i, j)] = d(i, j)
+    merges = []
+    while True:
+        best = (float('inf'), 2 ** 63 - 1)
+        for (i, j), v in M.items():
+            if alive[i] and alive[j]:
+                cand = (v, i * n + j)
+                if cand[0] < best[0] or (cand[0] == best[0] and cand[1] < best[1]):
+                    best = cand
+        got = exchange(struct.pack('<dq', best[0], best[1]))
+        v, idx = sharded.pick_global(got)
+        if idx == 2 ** 63 - 1 or not v <= threshold:
+            break
+        a, b = divmod(idx, n)
+        merges.append((a, b, v))
+        members[a] += members[b]
+        alive[b] = False
+        for k in range(n):
+            if alive[k] and k != a and (a + k) % world == rank:
+                M[(min(a, k), max(a, k))] = d(a, k)
+    return merges
+
+
+def _sharded_worker(rank, world, port, result_q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from spkdiar import sharded
+    rec = synth.make_recording(321, 6000, 3, turn_lo=2, turn_hi=4)
+    seg = [(t[0], t[1]) for t in rec.turns]
+    merges = _sharded_cpu_loop(rank, world, sharded.dist_exchange(), rec.frames, seg, 0.0)
+    dist.barrier()
+    result_q.put((rank, merges))
+    dist.destroy_process_group()
+
+
+def test_pick_global_order():
+    import struct
+    from spkdiar import sharded
+    nan = float('nan')
+    pk = lambda *c: b''.join(struct.pack('<dq', v, i) for v, i in c)
+    assert sharded.pick_global(pk((1.0, 5), (1.0, 3), (2.0, 1))) == (1.0, 3)          # ties: smaller flat index
+    v, i = sharded.pick_global(pk((1.0, 5), (nan, 9), (nan, 7), (-5.0, 1)))           # NaN first, first NaN wins
+    assert v != v and i == 7
+    assert sharded.pick_global(pk((float('inf'), 2 ** 63 - 1), (-float('inf'), 4))) == (-float('inf'), 4)
+
+
+@pytest.mark.timeout(600)
+def test_sharded_loop_two_gloo_ranks_equal_one():
+    from spkdiar import sharded
+    rec = synth.make_recording(321, 6000, 3, turn_lo=2, turn_hi=4)
+    seg = [(t[0], t[1]) for t in rec.turns]
+    single = _sharded_cpu_loop(0, 1, lambda mine: mine, rec.frames, seg, 0.0)
+    assert len(single) >= 5
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=540) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert got[0] == got[1] == single
