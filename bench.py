@@ -225,6 +225,99 @@ def workload_config():
             'parallelism': 'one recording per GPU, no collective'}
 
 
+def run_other_workload(args):
+    """The other BASELINE.json configurations (not the headline): one JSON line each, same
+    keys.  config3: agglomerative clustering of a 3-hour recording per GPU (weak scaling).
+    config4: a corpus of 10-minute recordings, file-sharded, change detection + clustering
+    through the drop-in API with host buffers (weak scaling).  config5: ONE long recording,
+    its pair matrix sharded over the GPUs, one 16-byte all-gather per merge (strong scaling)."""
+    import numpy as np
+    import torch
+    import spkdiar                                   # noqa: F401
+    from spkdiar import _abi, synth, corpus, sharded
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    ctx = _abi.Context(local, stream=torch.cuda.current_stream().cuda_stream)
+    W = max(args.warmup, 3)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == 'config3':
+        rec = synth.make_recording(1003 + rank, 1080000, 10, turn_lo=2, turn_hi=9)
+        sa, sb = [t[0] for t in rec.turns], [t[1] for t in rec.turns]
+        feat = ctx.upload(rec.frames)
+        hours_per_step, scaling = world * 3.0, 'weak'
+        desc = 'config3: CL1 agglomerative BIC clustering of a 3-hour recording (%d segments) per GPU' % len(sa)
+
+        def step():
+            with feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
+                return cl.run(0.0, 0, 1)[0]
+    elif args.workload == 'config5':
+        rec = synth.config5(n_frames=args.segments * 173)
+        sa, sb = [t[0] for t in rec.turns], [t[1] for t in rec.turns]
+        feat = ctx.upload(rec.frames)
+        ex = sharded.dist_exchange() if world > 1 else None
+        hours_per_step, scaling = rec.frames.shape[0] / RATE / 3600.0, 'strong'
+        desc = ('config5 (scaled): one %.1f-hour recording, %d segments, pair matrix dealt over %d GPU(s), '
+                '16-byte candidate all-gather per merge' % (hours_per_step, len(sa), world))
+
+        def step():
+            with feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
+                return cl.run_sharded(0.0, 0, rank, world, ex)[0]
+    else:
+        items = []
+        for k in range(args.files):
+            r = synth.config4_file(rank * args.files + k)
+            items.append(('c4_%d' % k, synth.one_line_recipe('/syn/c4_%d.wav' % k, r), r.frames))
+        hours_per_step, scaling = world * args.files * (60000 / RATE / 3600.0), 'weak'
+        desc = ('config4: %d ten-minute recordings per GPU, spk-diarization2 flags (gw BIC change detection + CL1), '
+                'host frames through the drop-in API' % args.files)
+
+        def step():
+            out = None
+            for name, lines, frames in items:
+                f = ctx.upload(frames)
+                try:
+                    out = corpus.diarize_recording(ctx, lines, lambda l: f, RATE)
+                finally:
+                    f.close()
+            return out
+    for _ in range(W):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    barrier()
+    value = args.steps * hours_per_step / (float(ms.item()) / 1e3)
+    if rank == 0:
+        print(json.dumps({'metric': 'audio_hours_per_sec_diarized', 'value': value, 'unit': 'audio-hours/s',
+                          'n_gpus': world, 'steps': args.steps, 'warmup': W,
+                          'ms_per_step': float(ms.item()) / args.steps, 'higher_is_better': True,
+                          'scaling': scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                          'config': {'workload': desc},
+                          'result': {'last': (len(res) if hasattr(res, '__len__') and not isinstance(res, tuple)
+                                              else res[2] if isinstance(res, tuple) else None)}}))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -233,9 +326,15 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-seconds', type=int, default=CPU_SAMPLE_SECONDS)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='config2', choices=['config2', 'config3', 'config4', 'config5'],
+                    help='config2 is the headline (BASELINE.json configs[1]); the others print their own line')
+    ap.add_argument('--segments', type=int, default=8000, help='config5: segments of the long recording')
+    ap.add_argument('--files', type=int, default=16, help='config4: recordings per GPU')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.workload != 'config2':
+        return run_other_workload(args)
 
     import numpy as np
     import torch
