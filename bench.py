@@ -49,6 +49,7 @@ GW_FLAGS = dict(winsize=1.0, winstep=3.0, deltaws=0.1)
 GLR_T = 1500.0
 KL2_T = 4000.0
 CPU_SAMPLE_SECONDS = 150            # audio seconds of the CPU-baseline sample
+SEQUENTIAL = bool(os.environ.get('SPKDIAR_BENCH_SEQUENTIAL'))      # one search after the other (for comparison)
 
 # algorithmic work per unit (restated in DESIGN.md)
 FLOP_LOGDET = 22893.0               # form 39x39 from prefix differences + factorise
@@ -120,8 +121,14 @@ def device_step(ctx, dev_ptr, nframes):
     feat = ctx.adopt(dev_ptr, nframes)
     out = {}
     try:
-        for name, met, thr in (('BIC', _abi.BIC, 0.0), ('GLR', _abi.GLR, GLR_T), ('KL2', _abi.KL2, KL2_T)):
-            win, _ = feat.gw_run([0], [nframes], float(RATE), W, ST, DW, thr, 1.0, met)
+        # the three searches are independent dependent chains: side by side on disjoint SM subsets
+        runs = [dict(rate=float(RATE), winsize=W, winstep=ST, deltaws=DW, threshold=thr, lambdac=1.0, metric=met)
+                for met, thr in ((_abi.BIC, 0.0), (_abi.GLR, GLR_T), (_abi.KL2, KL2_T))]
+        if SEQUENTIAL:
+            res = [feat.gw_run([0], [nframes], **r) for r in runs]
+        else:
+            res = feat.gw_run_multi([0], [nframes], runs)
+        for name, (win, _) in zip(('BIC', 'GLR', 'KL2'), res):
             out[name] = win
         sa, sb = segments_from_windows(out['BIC'], nframes)
         with feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
@@ -142,11 +149,16 @@ def e2e_step(ctx, host_frames, recipe_lines):
     feat = ctx.upload_ptr(host_frames.data_ptr(), host_frames.shape[0])
     texts = {}
     try:
-        for name, thr in (('BIC', 0.0), ('GLR', GLR_T), ('KL2', KL2_T)):
-            det = pcd.Detector(RATE, 'gw', name, GW_FLAGS['winsize'], GW_FLAGS['winstep'], GW_FLAGS['deltaws'],
-                               thr, 1.0, ctx=ctx)
-            buf = io.StringIO()
-            det.detect_changes(parsed, buf, loader=lambda l: feat)
+        names = ('BIC', 'GLR', 'KL2')
+        dets = [pcd.Detector(RATE, 'gw', name, GW_FLAGS['winsize'], GW_FLAGS['winstep'], GW_FLAGS['deltaws'],
+                             thr, 1.0, ctx=ctx) for name, thr in zip(names, (0.0, GLR_T, KL2_T))]
+        bufs = [io.StringIO() for _ in names]
+        if SEQUENTIAL:
+            for det, buf in zip(dets, bufs):
+                det.detect_changes(parsed, buf, loader=lambda l: feat)
+        else:
+            pcd.detect_changes_multi(dets, parsed, bufs, loader=lambda l: feat)
+        for name, buf in zip(names, bufs):
             texts[name] = buf.getvalue()
         cl = pcl.Clusterer(RATE, 1, 'hi', 'BIC', 0.0, 0, 1.3, ctx=ctx)
         buf = io.StringIO()

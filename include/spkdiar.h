@@ -174,6 +174,17 @@ int  spkdiar_gw_run(spkdiar_feat* f, const spkdiar_gw_params* params,
                     const int64_t* seg_a, const int64_t* seg_b, int32_t nchain,
                     spkdiar_gw_window* win, int64_t win_cap, int64_t* win_first);
 
+/* nrun searches over the SAME chains side by side (BASELINE config 2: the BIC, GLR and
+ * KL2 passes over one recipe): each search is one dependent chain of waves that is far
+ * from filling the GPU, so they run concurrently on disjoint subsets of the SMs.
+ * params[r], win[r], win_cap[r], win_first[r] belong to search r; results are exactly
+ * those of nrun separate spkdiar_gw_run calls. */
+#define SPKDIAR_MAX_RUNS 4
+int  spkdiar_gw_run_multi(spkdiar_feat* f, int32_t nrun, const spkdiar_gw_params* params,
+                          const int64_t* seg_a, const int64_t* seg_b, int32_t nchain,
+                          spkdiar_gw_window* const* win, const int64_t* win_cap,
+                          int64_t* const* win_first);
+
 /* ---- agglomerative clustering (K5-K7) ---------------------------------------
  * Replaces spk_cluster_hi of spk-clustering.py:178-260 (variant 1) and of
  * spk-clustering2.py:173-229 (variant 2).  Initial clusters are the frame

@@ -28,7 +28,7 @@ SYMBOLS = (
     'spkdiar_profile_read', 'spkdiar_features_upload', 'spkdiar_features_adopt',
     'spkdiar_stats_build', 'spkdiar_features_free', 'spkdiar_features_frames',
     'spkdiar_stats_window', 'spkdiar_score_windows', 'spkdiar_score_sets',
-    'spkdiar_gw_run', 'spkdiar_cluster_create', 'spkdiar_cluster_run',
+    'spkdiar_gw_run', 'spkdiar_gw_run_multi', 'spkdiar_cluster_create', 'spkdiar_cluster_run',
     'spkdiar_cluster_run_sharded', 'spkdiar_cluster_free', 'spkdiar_cluster_matrix',
 )
 
@@ -98,6 +98,8 @@ def load_library(path=None):
         'spkdiar_score_sets': (C.c_int, [vp, i64, pi64, pi64, pi64, pi64, pi64, pi64, C.c_int, dbl,
                                          pdbl, pdbl]),
         'spkdiar_gw_run': (C.c_int, [vp, C.POINTER(GwParams), pi64, pi64, i32, vp, i64, pi64]),
+        'spkdiar_gw_run_multi': (C.c_int, [vp, i32, C.POINTER(GwParams), pi64, pi64, i32, C.POINTER(vp), pi64,
+                                           C.POINTER(pi64)]),
         'spkdiar_cluster_create': (C.c_int, [vp, pi64, pi64, i64, C.c_int, dbl, C.POINTER(vp)]),
         'spkdiar_cluster_run': (C.c_int, [vp, dbl, i32, i32, vp, i64, pi64, pdbl]),
         'spkdiar_cluster_run_sharded': (C.c_int, [vp, dbl, i32, i32, i32, EXCHANGE_FN, vp, vp, i64,
@@ -268,6 +270,38 @@ class Features(object):
                 continue
             self.ctx._check(rc)
             return win[:int(first[nchain])], first
+
+    def gw_run_multi(self, seg_a, seg_b, runs, max_groups=0):
+        """Several growing-window searches over the same chains, side by side on disjoint SM
+        subsets.  ``runs``: list of dicts with the keyword arguments of ``gw_run`` (rate, winsize,
+        winstep, deltaws, threshold, lambdac, metric).  -> list of (records, win_first)."""
+        seg_a, seg_b = _i64(seg_a), _i64(seg_b)
+        nchain = seg_a.shape[0]
+        nrun = len(runs)
+        prm = (GwParams * nrun)(*[GwParams(float(r['rate']), float(r['winsize']), float(r['winstep']),
+                                           float(r['deltaws']), float(r['threshold']), float(r['lambdac']),
+                                           int(r['metric']), int(max_groups)) for r in runs])
+        caps = np.zeros(nrun, dtype=np.int64)
+        for k, r in enumerate(runs):
+            unit = max(float(r['rate']) / 2 - float(r['rate']) / 10, 1.0)
+            caps[k] = int(sum(2 * ((b - a) / unit + 2) for a, b in zip(seg_a, seg_b))) + 16
+        firsts = [np.zeros(nchain + 1, dtype=np.int64) for _ in range(nrun)]
+        while True:
+            wins = [np.zeros(int(caps[k]), dtype=GW_WINDOW_DTYPE) for k in range(nrun)]
+            wp = (C.c_void_p * nrun)(*[w.ctypes.data for w in wins])
+            fp = (C.POINTER(C.c_int64) * nrun)(*[_p(f, C.c_int64) for f in firsts])
+            rc = self.ctx.lib.spkdiar_gw_run_multi(self.h, nrun, prm, _p(seg_a, C.c_int64), _p(seg_b, C.c_int64),
+                                                   nchain, wp, _p(caps, C.c_int64), fp)
+            if rc == -4:                                # SPKDIAR_E_CAPACITY: retry with the needed sizes
+                grown = False
+                for k in range(nrun):
+                    if firsts[k][0] > caps[k]:
+                        caps[k] = int(firsts[k][0])
+                        grown = True
+                if grown:
+                    continue
+            self.ctx._check(rc)
+            return [(wins[k][:int(firsts[k][nchain])], firsts[k]) for k in range(nrun)]
 
     def cluster(self, seg_a, seg_b, metric, lambdac=1.3):
         seg_a, seg_b = _i64(seg_a), _i64(seg_b)

@@ -114,6 +114,7 @@ class Detector(object):
         self._own_ctx = ctx is None
         self.ctx = ctx if ctx is not None else _abi.Context(device)
         self.windows_visited = 0
+        self._prefetch = {}
 
     def close(self):
         if self._own_ctx and self.ctx is not None:
@@ -138,8 +139,11 @@ class Detector(object):
             return
         seg_a = [c[1] for c in chains]
         seg_b = [c[2] for c in chains]
-        win, first = feat.gw_run(seg_a, seg_b, self.rate, self.winsize, self.winstep, self.deltaws,
-                                 self.threshold, self.lambdac, self.metric)
+        got = self._prefetch.pop((id(feat), tuple(seg_a), tuple(seg_b)), None)     # detect_changes_multi
+        if got is None:
+            got = feat.gw_run(seg_a, seg_b, self.rate, self.winsize, self.winstep, self.deltaws,
+                              self.threshold, self.lambdac, self.metric)
+        win, first = got
         for k, (line, a, b) in enumerate(chains):
             self._gw_replay(feat, line, a, b, win[first[k]:first[k + 1]], outf, segf)
 
@@ -444,6 +448,41 @@ class Detector(object):
         if st.min_det_dist < MAXINT:
             log(p2line('Minimum between detected segments distance:', st.min_det_dist))
         log(p2line('Total detected speaker changes:', st.total_segments))
+
+
+def detect_changes_multi(detectors, recipe, outfs, loader):
+    """Several detectors (e.g. -d BIC, -d GLR and -d KL2 with otherwise the script's flags) over
+    the SAME recipe and resident features: the growing-window searches of all of them run side
+    by side on the GPU (``spkdiar_gw_run_multi``), then every detector replays its own records
+    exactly as ``detect_changes`` does.  Outputs are identical to calling ``detect_changes`` on
+    each detector in turn."""
+    dets = [d for d in detectors if d.method == 'gw' and not d.tt and d.gw_on_device]
+    if len(dets) >= 2 and len({d.rate for d in dets}) == 1:
+        groups = []
+        this_wav = this_lna = ''
+        feat = None
+        chains = []
+        for line in recipe:                                  # the walk of detect_changes (CD:360-374)
+            if line.audio != this_wav:
+                if chains:
+                    groups.append((feat, chains))
+                    chains = []
+                this_wav = line.audio
+                feat = loader(line)
+            if line.lna != this_lna:
+                this_lna = line.lna
+                chains.append(dets[0]._bounds(line, feat.n))
+        if chains:
+            groups.append((feat, chains))
+        for feat, ch in groups:
+            seg_a = [c[0] for c in ch]
+            seg_b = [c[1] for c in ch]
+            runs = [dict(rate=d.rate, winsize=d.winsize, winstep=d.winstep, deltaws=d.deltaws,
+                         threshold=d.threshold, lambdac=d.lambdac, metric=d.metric) for d in dets]
+            for d, r in zip(dets, feat.gw_run_multi(seg_a, seg_b, runs)):
+                d._prefetch[(id(feat), tuple(seg_a), tuple(seg_b))] = r
+    for d, outf in zip(detectors, outfs):
+        d.detect_changes(recipe, outf, loader=loader)
 
 
 def build_parser():

@@ -36,6 +36,10 @@ struct spkdiar_ctx {
     // hundreds of milliseconds per recording; blocks are kept and reused by later calls
     struct Block { void* p; size_t bytes; bool used; };
     std::vector<Block> pool;
+    // streams of concurrent growing-window searches (spkdiar_gw_run_multi)
+    cudaStream_t aux[SPKDIAR_MAX_RUNS] = {nullptr};
+    cudaEvent_t aux_done[SPKDIAR_MAX_RUNS] = {nullptr};
+    int naux = 0;
 };
 
 struct spkdiar_feat {

@@ -103,6 +103,7 @@ void spkdiar_destroy(spkdiar_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    for (int r = 0; r < c->naux; ++r) { cudaStreamSynchronize(c->aux[r]); cudaEventDestroy(c->aux_done[r]); cudaStreamDestroy(c->aux[r]); }
     pool_destroy(c);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;

@@ -227,3 +227,22 @@ def test_adopt_device_memory_equals_upload(ctx, rec):
     finally:
         fa.close()
         fu.close()
+
+
+def test_gw_run_multi_equals_separate_runs(ctx):
+    """BIC, GLR and KL2 searches side by side on disjoint SM subsets == one after the other
+    (records byte-identical: the decisions do not depend on how many CTAs work on a chain)."""
+    rec = synth.make_recording(11, 24000, 4)
+    f = ctx.upload(rec.frames)
+    try:
+        runs = [dict(rate=100.0, winsize=100.0, winstep=300.0, deltaws=10.0, threshold=t, lambdac=1.0, metric=m)
+                for m, t in ((_abi.BIC, 0.0), (_abi.GLR, 1500.0), (_abi.KL2, 4000.0))]
+        seg_a, seg_b = [0, 9000, 9100], [9000, 9100, 24000]          # three chains, one too short for a window
+        sep = [f.gw_run(seg_a, seg_b, **r) for r in runs]
+        mul = f.gw_run_multi(seg_a, seg_b, runs)
+        for (w0, f0), (w1, f1) in zip(sep, mul):
+            assert len(w0) > 0
+            assert w0.tobytes() == w1.tobytes()
+            assert np.array_equal(f0, f1)
+    finally:
+        f.close()
