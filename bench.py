@@ -21,7 +21,7 @@ pinned HOST memory, the host->device copy and the host-side replay inside the
 timed region.
 
 N > 1 (torchrun): recordings are independent, so every rank diarizes its own
-1-hour recording (seed 1002 + rank) with no data-path collective - weak scaling.
+copy of the 1-hour recording (seed 1002) with no data-path collective - weak scaling.
 
 `--impl reference` times the reference's own CPU implementation (the oracle: the
 reference scripts are Python 2 and cannot run here; the oracle is their
@@ -58,9 +58,11 @@ BYTES_STATS_PER_FRAME = 2 * 156 + 6560
 
 
 def make_recording(rank):
+    """Every rank gets the SAME synthetic recording (seed 1002): weak scaling with identical work per
+    GPU, so that the per-N values measure the machine and not the luck of a seed."""
     import spkdiar                                   # noqa: F401
     from spkdiar import synth
-    return synth.make_recording(1002 + rank, FRAMES, 8, rate=RATE)
+    return synth.make_recording(1002, FRAMES, 8, rate=RATE)
 
 
 class ClockSampler(object):
@@ -234,7 +236,7 @@ def workload_config():
                         'BIC+GLR+KL2 change detection + CL1 BIC clustering of the BIC turns',
             'frames': FRAMES, 'dim': 39, 'frame_rate': RATE, 'glr_threshold': GLR_T, 'kl2_threshold': KL2_T,
             'l2': 'inputs larger than L2: 2.36 GB of prefix records rewritten and re-read every step (L2 = 126 MB)',
-            'parallelism': 'one recording per GPU, no collective'}
+            'parallelism': 'one recording per GPU (every rank the same synthetic recording), no data-path collective'}
 
 
 def run_other_workload(args):

@@ -226,6 +226,16 @@ int  spkdiar_cluster_run_sharded(spkdiar_clus* c, double threshold,
                                  spkdiar_exchange_fn exchange, void* user,
                                  spkdiar_merge* out, int64_t cap,
                                  int64_t* nmerges, double* stats4);
+/* The same run with the exchange done by NCCL on the context's stream (libnccl.so.2 is
+ * loaded at run time, e.g. the copy torch ships): merges are queued in batches of
+ * argmin kernel -> ncclAllGather of the 16-byte candidates -> deciding + rescoring kernel,
+ * the host only looks at a stop flag between batches.  Rank 0 creates the id with
+ * spkdiar_nccl_unique_id() and the caller distributes its 128 bytes to all ranks. */
+int  spkdiar_nccl_unique_id(void* out128);
+int  spkdiar_cluster_run_sharded_nccl(spkdiar_clus* c, double threshold, int32_t max_spk,
+                                      int32_t rank, int32_t nranks, const void* unique_id128,
+                                      spkdiar_merge* out, int64_t cap, int64_t* nmerges,
+                                      double* stats4);
 int  spkdiar_cluster_free(spkdiar_clus* c);
 /* test hook: copy the current pair matrix (nseg x nseg, row-major, entries of
  * dead rows / columns undefined) and the alive flags to the host */

@@ -29,7 +29,8 @@ SYMBOLS = (
     'spkdiar_stats_build', 'spkdiar_features_free', 'spkdiar_features_frames',
     'spkdiar_stats_window', 'spkdiar_score_windows', 'spkdiar_score_sets',
     'spkdiar_gw_run', 'spkdiar_gw_run_multi', 'spkdiar_cluster_create', 'spkdiar_cluster_run',
-    'spkdiar_cluster_run_sharded', 'spkdiar_cluster_free', 'spkdiar_cluster_matrix',
+    'spkdiar_cluster_run_sharded', 'spkdiar_cluster_run_sharded_nccl', 'spkdiar_nccl_unique_id',
+    'spkdiar_cluster_free', 'spkdiar_cluster_matrix',
 )
 
 
@@ -104,6 +105,8 @@ def load_library(path=None):
         'spkdiar_cluster_run': (C.c_int, [vp, dbl, i32, i32, vp, i64, pi64, pdbl]),
         'spkdiar_cluster_run_sharded': (C.c_int, [vp, dbl, i32, i32, i32, EXCHANGE_FN, vp, vp, i64,
                                                   pi64, pdbl]),
+        'spkdiar_cluster_run_sharded_nccl': (C.c_int, [vp, dbl, i32, i32, i32, vp, vp, i64, pi64, pdbl]),
+        'spkdiar_nccl_unique_id': (C.c_int, [vp]),
         'spkdiar_cluster_free': (C.c_int, [vp]),
         'spkdiar_cluster_matrix': (C.c_int, [vp, pdbl, C.POINTER(C.c_uint8)]),
     }
@@ -116,6 +119,16 @@ def load_library(path=None):
     if path == os.environ.get('SPKDIAR_LIB', LIB_PATH):
         _lib = lib
     return lib
+
+
+def nccl_unique_id():
+    """128 bytes identifying a new NCCL communicator (call on rank 0, send to every rank)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.spkdiar_nccl_unique_id(buf)
+    if rc != 0:
+        raise SpkdiarError(rc, 'NCCL is not available (libnccl.so.2 could not be loaded)')
+    return buf.raw
 
 
 class Context(object):
@@ -358,6 +371,18 @@ class Clusters(object):
         cb = EXCHANGE_FN(_cb)
         self.ctx._check(self.ctx.lib.spkdiar_cluster_run_sharded(
             self.h, float(threshold), int(max_spk), int(rank), int(nranks), cb, None,
+            out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(nm), _p(stats, C.c_double)))
+        return out[:nm.value], stats
+
+    def run_sharded_nccl(self, threshold, max_spk, rank, nranks, unique_id):
+        """The sharded run with NCCL called by the library on its own stream; ``unique_id``:
+        the 128 bytes of ``nccl_unique_id()`` made on rank 0 (None when nranks == 1)."""
+        out = np.zeros(max(self.n, 1), dtype=MERGE_DTYPE)
+        nm = C.c_int64(0)
+        stats = np.zeros(4)
+        idbuf = C.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
+        self.ctx._check(self.ctx.lib.spkdiar_cluster_run_sharded_nccl(
+            self.h, float(threshold), int(max_spk), int(rank), int(nranks), idbuf,
             out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(nm), _p(stats, C.c_double)))
         return out[:nm.value], stats
 

@@ -172,6 +172,10 @@ struct ClDev {
     double* pend;                // [REC + 2] merged record, ln|S_ab|, index a (+1; 0 = nothing pending)
     ClBest* local_best;          // this rank's candidate of the current iteration
     unsigned int* ticket;        // last-CTA election of the argmin kernel
+    // device-decided run (NCCL exchange on the stream, no host round trip per merge)
+    int* stopped;                // set when the stop test fails; later launches return at once
+    const ClBest* gathered;      // [nranks] candidates of all ranks (all-gather target)
+    double* det;                 // [0] max_det [1] min_det
 };
 
 __device__ __forceinline__ void cl_grid_barrier(unsigned long long* ctr, unsigned long long& target) {
@@ -509,6 +513,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
 // ---- the same two phases as separate launches (row-sharded run: the host exchanges the ranks'
 // candidates between them) ----
 __global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_argmin(const ClDev g, long long nm) {
+    if (g.stopped && *((volatile int*)g.stopped)) return;
     extern __shared__ __align__(16) unsigned char cl_smem[];
     const ClSmem sm = cl_carve(cl_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -574,6 +579,54 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_apply(const ClDev g, l
     }
 }
 
+// cl_shard_apply with the decision taken on the device: every thread picks the global minimum of
+// the gathered candidates (ndarray.argmin order) and evaluates the stop test of CL1:207-208
+__global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_apply_dev(const ClDev g, long long nm) {
+    if (*((volatile int*)g.stopped)) return;
+    ClBest best{__ldcg(&g.gathered[0].v), __ldcg((const long long*)&g.gathered[0].idx)};
+    for (int r = 1; r < g.nranks; ++r)
+        cl_take(best, __ldcg(&g.gathered[r].v), __ldcg((const long long*)&g.gathered[r].idx));
+    const int64_t n = g.n;
+    const double mind = best.v;
+    const int64_t bi = best.idx / n, bj = best.idx - (best.idx / n) * n;
+    const int64_t a = bi < bj ? bi : bj, b = bi < bj ? bj : bi;
+    const int64_t nalive = n - nm;
+    const bool go = (mind <= g.threshold) || (g.max_spk > 0 && nalive > (int64_t)g.max_spk);
+    if (!go || a == b || best.idx == INT64_MAX) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { *g.final_min = mind; __threadfence(); *g.stopped = 1; }
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (nm < g.cap) { spkdiar_merge mr; mr.a = (int32_t)a; mr.b = (int32_t)b; mr.d = mind; g.out[nm] = mr; }
+        *g.nmerge = nm + 1;
+        if (mind > g.det[0]) g.det[0] = mind;               // spk-clustering.py:210-213
+        if (mind < g.det[1]) g.det[1] = mind;
+    }
+    extern __shared__ __align__(16) unsigned char cl_smem[];
+    const ClSmem sm = cl_carve(cl_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t gwarp = (int64_t)warp * gridDim.x + blockIdx.x;
+    const int64_t nwarps = (int64_t)gridDim.x * CL_WARPS;
+    const int nwords = (int)((g.n + 31) / 32);
+    for (int wd = threadIdx.x; wd < nwords; wd += CL_THREADS) {
+        uint32_t w = g.abits_g[wd];
+        if (wd == (int)(b >> 5)) w &= ~(1u << (b & 31));
+        sm.abits[wd] = w;
+    }
+    for (int q = threadIdx.x; q < REC; q += CL_THREADS)
+        sm.merged[q] = __ldcg(g.rec + a * REC + q) + __ldcg(g.rec + b * REC + q);
+    __syncthreads();
+    const double ld_ab = cl_phase_apply(g, nm, a, b, sm, warp, lane, gwarp, nwarps);
+    if (blockIdx.x == 0) {
+        for (int q = threadIdx.x; q < REC; q += CL_THREADS) g.pend[q] = sm.merged[q];
+        if (threadIdx.x == 0) {
+            g.pend[REC] = ld_ab;
+            g.pend[REC + 1] = (double)(a + 1);
+            atomicAnd(g.abits_g + (b >> 5), ~(1u << (b & 31)));
+        }
+    }
+}
+
 // initial fill of the pairs this rank owns (nranks > 1)
 __global__ void __launch_bounds__(SC_THREADS, 3)
 cl_fill_pairs_shard(const double* rec, const double* __restrict__ ld, int64_t n, int metric, double lambda,
@@ -622,6 +675,8 @@ inline cudaError_t cluster_configure() {
     e = cudaFuncSetAttribute(cl_shard_argmin, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(cl_shard_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(cl_shard_apply_dev, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(cl_fill_pairs_shard, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
     if (e != cudaSuccess) return e;

@@ -7,6 +7,8 @@
 // Build (see __graft_entry__.build()):
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
 //        -shared -Xcompiler -fPIC -o libspkdiar.so spkdiar.cu
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <limits>

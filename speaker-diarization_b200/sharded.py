@@ -82,14 +82,29 @@ def pick_global(candidates):
     return float(best[0]), int(best[1])
 
 
+def broadcast_nccl_id(group=None):
+    """A fresh NCCL unique id made on rank 0 and sent to all ranks of a torch.distributed job.
+    An id makes ONE communicator: call this once per ``cluster_sharded`` run."""
+    import torch.distributed as dist
+    from . import _abi
+    box = [_abi.nccl_unique_id() if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
 def cluster_sharded(ctx, frames_or_feat, seg_a, seg_b, metric, lambdac, threshold, max_spk,
-                    rank, nranks, exchange):
-    """Run this rank's share; -> (merges, stats) identical on every rank."""
+                    rank, nranks, exchange=None, nccl_id=None, device_loop=False):
+    """Run this rank's share; -> (merges, stats) identical on every rank.  With ``nccl_id``
+    (see ``broadcast_nccl_id``) the library exchanges the candidates itself over NCCL, on its
+    stream (``device_loop=True`` selects that loop for a single rank, where nothing is exchanged);
+    else ``exchange`` is called once per merge."""
     from . import _abi
     own = not isinstance(frames_or_feat, _abi.Features)
     feat = ctx.upload(frames_or_feat) if own else frames_or_feat
     try:
         with feat.cluster(seg_a, seg_b, metric, lambdac) as cl:
+            if nccl_id is not None or device_loop:
+                return cl.run_sharded_nccl(threshold, max_spk, rank, nranks, nccl_id)
             return cl.run_sharded(threshold, max_spk, rank, nranks, exchange)
     finally:
         if own:

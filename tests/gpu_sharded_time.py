@@ -17,6 +17,8 @@ rank = int(os.environ.get('RANK', '0'))
 local = int(os.environ.get('LOCAL_RANK', '0'))
 torch.cuda.set_device(local)
 ex = None
+nid = None
+mode = os.environ.get('SPKDIAR_SHARD_MODE', 'nccl')
 if world > 1:
     import torch.distributed as dist
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
@@ -28,17 +30,22 @@ ctx = _abi.Context(local)
 f = ctx.upload(rec.frames)
 for rep in range(2):
     if world > 1:
+        if mode == 'nccl':
+            nid = sharded.broadcast_nccl_id()      # an id makes ONE communicator
         dist.barrier()
     torch.cuda.synchronize()
     ctx.profile(True)
     t0 = time.perf_counter()
     with f.cluster(a, b, _abi.BIC, 1.3) as cl:
-        merges, stats = cl.run_sharded(0.0, 0, rank, world, ex)
+        if mode == 'nccl':
+            merges, stats = cl.run_sharded_nccl(0.0, 0, rank, world, nid)
+        else:
+            merges, stats = cl.run_sharded(0.0, 0, rank, world, ex)
     dt = time.perf_counter() - t0
     prof = ctx.profile_read()
     ctx.profile(False)
 hours = rec.frames.shape[0] / 100.0 / 3600.0
-print('rank %d/%d: segments %d merges %d speakers %d  wall %.1f ms (fill %.1f ms, merge kernels %.1f ms)  %.2f audio-h/s  sha %s'
+print(mode, 'rank %d/%d: segments %d merges %d speakers %d  wall %.1f ms (fill %.1f ms, merge kernels %.1f ms)  %.2f audio-h/s  sha %s'
       % (rank, world, len(a), len(merges), len(a) - len(merges), dt * 1e3, prof['score'][0], prof['merge'][0],
          hours / dt, hashlib.sha256(merges.tobytes()).hexdigest()[:12]), flush=True)
 if world > 1:

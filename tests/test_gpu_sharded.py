@@ -57,3 +57,16 @@ def test_sharded_equals_resident(metric, nranks):
     for m, st in res:
         assert m.tobytes() == ref_m.tobytes()
         assert np.array_equal(st, ref_st)
+
+
+def test_device_decided_loop_equals_resident():
+    """The NCCL variant's loop (argmin kernel -> gather -> deciding + rescoring kernel, merges queued in
+    batches, stop flag on the device) with a single rank: no exchange, same merges."""
+    rec = synth.make_recording(78, 30000, 6, turn_lo=1, turn_hi=4)
+    a = [t[0] for t in rec.turns]
+    b = [t[1] for t in rec.turns]
+    ref_m, ref_st = _single(rec, a, b, _abi.BIC, 0.0, 0)
+    with _abi.Context(0) as ctx:
+        m, st = sharded.cluster_sharded(ctx, rec.frames, a, b, _abi.BIC, 1.3, 0.0, 0, 0, 1, device_loop=True)
+    assert len(ref_m) > 20 and m.tobytes() == ref_m.tobytes()
+    assert np.array_equal(st, ref_st)
