@@ -279,14 +279,17 @@ def run_other_workload(args):
         rec = synth.config5(n_frames=args.segments * 173)
         sa, sb = [t[0] for t in rec.turns], [t[1] for t in rec.turns]
         feat = ctx.upload(rec.frames)
-        ex = sharded.dist_exchange() if world > 1 else None
+        mbx = sharded.Mailboxes(ctx) if world > 1 else None
         hours_per_step, scaling = rec.frames.shape[0] / RATE / 3600.0, 'strong'
-        desc = ('config5 (scaled): one %.1f-hour recording, %d segments, pair matrix dealt over %d GPU(s), '
-                '16-byte candidate all-gather per merge' % (hours_per_step, len(sa), world))
+        desc = ('config5 (scaled): one %.1f-hour recording, %d segments, pair matrix dealt over %d GPU(s), one '
+                'persistent kernel per GPU, 16-byte candidates exchanged through peer-memory mailboxes per merge'
+                % (hours_per_step, len(sa), world))
 
         def step():
             with feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
-                return cl.run_sharded(0.0, 0, rank, world, ex)[0]
+                if world > 1:
+                    return cl.run_sharded_p2p(0.0, 0, rank, world, mbx.ptrs, mbx.next_base(len(sa)))[0]
+                return cl.run(0.0, 0, 1)[0]
     else:
         items = []
         for k in range(args.files):

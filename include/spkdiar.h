@@ -236,6 +236,24 @@ int  spkdiar_cluster_run_sharded_nccl(spkdiar_clus* c, double threshold, int32_t
                                       int32_t rank, int32_t nranks, const void* unique_id128,
                                       spkdiar_merge* out, int64_t cap, int64_t* nmerges,
                                       double* stats4);
+/* The same run as ONE persistent kernel per rank whose ranks exchange their candidates
+ * through peer memory (NVLink): every rank owns a mailbox of 2 x nranks 32-byte slots;
+ * per merge, CTA 0 of a rank stores its candidate into its slot of EVERY rank's mailbox
+ * (payload, then a sequence number with st.release.sys) and all CTAs poll their own
+ * device's mailbox (ld.acquire.sys) - no host round trip, no collective library call.
+ * mailboxes[r] is rank r's mailbox as mapped on this device (spkdiar_mailbox_open of the
+ * handle rank r made with spkdiar_mailbox_create; mailboxes[rank] is the local pointer).
+ * seq_base: every rank passes the same value, larger by at least nseg + 2 than in the
+ * previous run on the same mailboxes.  The ranks' kernels must run at the same time, on
+ * different devices; a rank that waits longer than ~1e8 polls gives up with an error. */
+int  spkdiar_mailbox_create(spkdiar_ctx* ctx, int32_t nranks, void** local_ptr, void* ipc_handle64);
+int  spkdiar_mailbox_open(spkdiar_ctx* ctx, const void* ipc_handle64, void** peer_ptr);
+int  spkdiar_mailbox_close(spkdiar_ctx* ctx, void* peer_ptr);
+int  spkdiar_mailbox_free(spkdiar_ctx* ctx, void* local_ptr);
+int  spkdiar_cluster_run_sharded_p2p(spkdiar_clus* c, double threshold, int32_t max_spk,
+                                     int32_t rank, int32_t nranks, void* const* mailboxes,
+                                     uint64_t seq_base, spkdiar_merge* out, int64_t cap,
+                                     int64_t* nmerges, double* stats4);
 int  spkdiar_cluster_free(spkdiar_clus* c);
 /* test hook: copy the current pair matrix (nseg x nseg, row-major, entries of
  * dead rows / columns undefined) and the alive flags to the host */

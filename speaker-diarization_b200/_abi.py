@@ -30,6 +30,8 @@ SYMBOLS = (
     'spkdiar_stats_window', 'spkdiar_score_windows', 'spkdiar_score_sets',
     'spkdiar_gw_run', 'spkdiar_gw_run_multi', 'spkdiar_cluster_create', 'spkdiar_cluster_run',
     'spkdiar_cluster_run_sharded', 'spkdiar_cluster_run_sharded_nccl', 'spkdiar_nccl_unique_id',
+    'spkdiar_cluster_run_sharded_p2p', 'spkdiar_mailbox_create', 'spkdiar_mailbox_open',
+    'spkdiar_mailbox_close', 'spkdiar_mailbox_free',
     'spkdiar_cluster_free', 'spkdiar_cluster_matrix',
 )
 
@@ -107,6 +109,12 @@ def load_library(path=None):
                                                   pi64, pdbl]),
         'spkdiar_cluster_run_sharded_nccl': (C.c_int, [vp, dbl, i32, i32, i32, vp, vp, i64, pi64, pdbl]),
         'spkdiar_nccl_unique_id': (C.c_int, [vp]),
+        'spkdiar_cluster_run_sharded_p2p': (C.c_int, [vp, dbl, i32, i32, i32, C.POINTER(vp), C.c_uint64, vp, i64, pi64,
+                                                      pdbl]),
+        'spkdiar_mailbox_create': (C.c_int, [vp, i32, C.POINTER(vp), vp]),
+        'spkdiar_mailbox_open': (C.c_int, [vp, vp, C.POINTER(vp)]),
+        'spkdiar_mailbox_close': (C.c_int, [vp, vp]),
+        'spkdiar_mailbox_free': (C.c_int, [vp, vp]),
         'spkdiar_cluster_free': (C.c_int, [vp]),
         'spkdiar_cluster_matrix': (C.c_int, [vp, pdbl, C.POINTER(C.c_uint8)]),
     }
@@ -383,6 +391,18 @@ class Clusters(object):
         idbuf = C.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
         self.ctx._check(self.ctx.lib.spkdiar_cluster_run_sharded_nccl(
             self.h, float(threshold), int(max_spk), int(rank), int(nranks), idbuf,
+            out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(nm), _p(stats, C.c_double)))
+        return out[:nm.value], stats
+
+    def run_sharded_p2p(self, threshold, max_spk, rank, nranks, mailbox_ptrs, seq_base):
+        """The sharded run as one persistent kernel per rank with the exchange through peer
+        memory; ``mailbox_ptrs``: device pointers (ints) of all ranks' mailboxes as mapped here."""
+        out = np.zeros(max(self.n, 1), dtype=MERGE_DTYPE)
+        nm = C.c_int64(0)
+        stats = np.zeros(4)
+        arr = (C.c_void_p * max(nranks, 1))(*[C.c_void_p(p) for p in (mailbox_ptrs or [0])])
+        self.ctx._check(self.ctx.lib.spkdiar_cluster_run_sharded_p2p(
+            self.h, float(threshold), int(max_spk), int(rank), int(nranks), arr, int(seq_base),
             out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(nm), _p(stats, C.c_double)))
         return out[:nm.value], stats
 

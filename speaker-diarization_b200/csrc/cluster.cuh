@@ -149,6 +149,21 @@ cl_fill_pairs(const double* rec, const double* __restrict__ ld, int64_t n, int m
     }
 }
 
+// One mailbox slot per (parity, sending rank): the sender writes the payload, then the sequence
+// number with release semantics at system scope; the receiver polls the sequence number with
+// acquire semantics.  Slots live in the RECEIVER's memory, senders write them through
+// peer-mapped pointers (NVLink).
+struct ClMail { double v; long long idx; unsigned long long seq; unsigned long long pad; };
+constexpr int CL_MAX_RANKS = 16;
+__device__ __forceinline__ void cl_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long cl_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 struct ClDev {
     double* rec; double* ld; double* M; uint8_t* alive_out;
     int64_t n;
@@ -176,6 +191,10 @@ struct ClDev {
     int* stopped;                // set when the stop test fails; later launches return at once
     const ClBest* gathered;      // [nranks] candidates of all ranks (all-gather target)
     double* det;                 // [0] max_det [1] min_det
+    // peer-memory exchange inside the persistent kernel
+    ClMail* mbox[CL_MAX_RANKS];  // mbox[r]: rank r's mailbox [2][nranks] as mapped on THIS device (mbox[rank]: local)
+    unsigned long long seq_base; // sequence numbers of this run start above it
+    int* err;                    // set when a peer did not answer in time
 };
 
 __device__ __forceinline__ void cl_grid_barrier(unsigned long long* ctr, unsigned long long& target) {
@@ -463,6 +482,37 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
                 cl_take(b, v, i);
             }
             b = cl_warp_best(b);
+            if (g.nranks > 1) {
+                // ---------- exchange with the other ranks through peer memory ----------
+                // CTA 0 posts this rank's candidate into every rank's mailbox (lane r -> rank r);
+                // EVERY CTA then reads its own device's mailbox until all candidates of this
+                // iteration have arrived, and takes the global minimum in ndarray.argmin order.
+                b.v = __shfl_sync(0xffffffffu, b.v, 0);
+                b.idx = __shfl_sync(0xffffffffu, (long long)b.idx, 0);
+                const unsigned long long want = g.seq_base + (unsigned long long)nm + 1ULL;
+                const int slot = (int)(nm & 1) * g.nranks;
+                if (blockIdx.x == 0 && lane < g.nranks) {
+                    ClMail* dst = g.mbox[lane] + slot + g.rank;
+                    dst->v = b.v; dst->idx = b.idx;
+                    cl_st_release_sys(&dst->seq, want);
+                }
+                ClBest got{d_inf(), INT64_MAX};
+                bool late = false;
+                if (lane < g.nranks) {
+                    const ClMail* src = g.mbox[g.rank] + slot + lane;
+                    long long spins = 0;
+                    while (cl_ld_acquire_sys(&src->seq) != want) {
+                        if (++spins > 20000000LL || *((volatile int*)g.err)) { late = true; break; }
+                    }
+                    got.v = *((volatile const double*)&src->v);
+                    got.idx = *((volatile const long long*)&src->idx);
+                }
+                if (__any_sync(0xffffffffu, late)) {
+                    if (lane == 0) *g.err = 1;
+                    got.v = d_inf(); got.idx = INT64_MAX;          // stops the loop below (a == b)
+                }
+                b = cl_warp_best(got);
+            }
             if (lane == 0) gbest = b;
         }
         __syncthreads();
@@ -471,7 +521,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
         const int64_t a = bi < bj ? bi : bj, b = bi < bj ? bj : bi;
         // ---------- stop test, spk-clustering.py:207-208 ----------
         const bool go = (mind <= g.threshold) || (g.max_spk > 0 && nalive > (int64_t)g.max_spk);
-        if (!go || a == b) {
+        if (!go || a == b || gbest.idx == INT64_MAX) {
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 if (g.dbg) { g.dbg[0] = t_scan; g.dbg[1] = t_b1; g.dbg[2] = t_pick; g.dbg[3] = t_score; g.dbg[4] = t_b2; g.dbg[5] = nm; }
                 *g.nmerge = nm;
@@ -503,6 +553,37 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
         }
         --nalive;
         ++nm;
+    }
+    if (g.nranks > 1 && blockIdx.x == 0 && warp == 0 && !*((volatile int*)g.err)) {
+        // one more round: (max, min) over every finite distance any rank computed.  All ranks left the
+        // loop at the same iteration, so the sequence number nm + 2 and the slot parity agree.
+        const unsigned long long want = g.seq_base + (unsigned long long)nm + 2ULL;
+        const int slot = (int)((nm + 1) & 1) * g.nranks;
+        const unsigned long long kmax = __ldcg(g.stat + 0), kmin = __ldcg(g.stat + 1);
+        if (lane < g.nranks) {
+            ClMail* dst = g.mbox[lane] + slot + g.rank;
+            dst->v = __longlong_as_double((long long)kmax); dst->idx = (long long)kmin;
+            cl_st_release_sys(&dst->seq, want);
+        }
+        unsigned long long gmax = kmax, gmin = kmin;
+        bool late = false;
+        if (lane < g.nranks) {
+            const ClMail* src = g.mbox[g.rank] + slot + lane;
+            long long spins = 0;
+            while (cl_ld_acquire_sys(&src->seq) != want) { if (++spins > 20000000LL) { late = true; break; } }
+            gmax = (unsigned long long)__double_as_longlong(*((volatile const double*)&src->v));
+            gmin = (unsigned long long)*((volatile const long long*)&src->idx);
+        }
+        if (__any_sync(0xffffffffu, late)) {
+            if (lane == 0) *g.err = 1;
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {                       // ordered keys: plain integer max / min
+                const unsigned long long om = __shfl_xor_sync(0xffffffffu, gmax, o), on = __shfl_xor_sync(0xffffffffu, gmin, o);
+                gmax = om > gmax ? om : gmax; gmin = on < gmin ? on : gmin;
+            }
+            if (lane == 0) { g.stat[0] = gmax; g.stat[1] = gmin; }
+        }
     }
     if (blockIdx.x == 0) {
         __syncthreads();

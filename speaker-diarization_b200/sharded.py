@@ -92,17 +92,62 @@ def broadcast_nccl_id(group=None):
     return box[0]
 
 
+class Mailboxes(object):
+    """The peer-memory mailboxes of a torch.distributed job (one process per GPU): every rank
+    creates its own, the CUDA IPC handles are all-gathered, every rank maps the others'.  Use one
+    object for many runs (``next_base`` hands out the sequence-number bases)."""
+
+    def __init__(self, ctx, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        self.ctx = ctx
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        local = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        ctx._check(ctx.lib.spkdiar_mailbox_create(ctx.h, self.world, C.byref(local), handle))
+        self.local = local.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.ptrs = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.local)
+            else:
+                p = C.c_void_p()
+                ctx._check(ctx.lib.spkdiar_mailbox_open(ctx.h, C.create_string_buffer(h, 64), C.byref(p)))
+                self.ptrs.append(p.value)
+        self._base = 0
+        dist.barrier(group)
+
+    def next_base(self, nseg):
+        base = self._base
+        self._base += int(nseg) + 4
+        return base
+
+    def close(self):
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank:
+                self.ctx.lib.spkdiar_mailbox_close(self.ctx.h, p)
+        self.ctx.lib.spkdiar_mailbox_free(self.ctx.h, self.local)
+        self.ptrs = []
+
+
 def cluster_sharded(ctx, frames_or_feat, seg_a, seg_b, metric, lambdac, threshold, max_spk,
-                    rank, nranks, exchange=None, nccl_id=None, device_loop=False):
+                    rank, nranks, exchange=None, nccl_id=None, device_loop=False, mailboxes=None):
     """Run this rank's share; -> (merges, stats) identical on every rank.  With ``nccl_id``
     (see ``broadcast_nccl_id``) the library exchanges the candidates itself over NCCL, on its
     stream (``device_loop=True`` selects that loop for a single rank, where nothing is exchanged);
-    else ``exchange`` is called once per merge."""
+    with ``mailboxes`` (a ``Mailboxes``) the exchange happens inside one persistent kernel per rank
+    through peer memory; else ``exchange`` is called once per merge."""
     from . import _abi
     own = not isinstance(frames_or_feat, _abi.Features)
     feat = ctx.upload(frames_or_feat) if own else frames_or_feat
     try:
         with feat.cluster(seg_a, seg_b, metric, lambdac) as cl:
+            if mailboxes is not None:
+                return cl.run_sharded_p2p(threshold, max_spk, rank, nranks, mailboxes.ptrs,
+                                          mailboxes.next_base(len(seg_a)))
             if nccl_id is not None or device_loop:
                 return cl.run_sharded_nccl(threshold, max_spk, rank, nranks, nccl_id)
             return cl.run_sharded(threshold, max_spk, rank, nranks, exchange)

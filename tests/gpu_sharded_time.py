@@ -18,6 +18,7 @@ local = int(os.environ.get('LOCAL_RANK', '0'))
 torch.cuda.set_device(local)
 ex = None
 nid = None
+mbx = None
 mode = os.environ.get('SPKDIAR_SHARD_MODE', 'nccl')
 if world > 1:
     import torch.distributed as dist
@@ -28,6 +29,8 @@ a = [t[0] for t in rec.turns]
 b = [t[1] for t in rec.turns]
 ctx = _abi.Context(local)
 f = ctx.upload(rec.frames)
+if world > 1 and mode == 'p2p':
+    mbx = sharded.Mailboxes(ctx)
 for rep in range(2):
     if world > 1:
         if mode == 'nccl':
@@ -37,7 +40,9 @@ for rep in range(2):
     ctx.profile(True)
     t0 = time.perf_counter()
     with f.cluster(a, b, _abi.BIC, 1.3) as cl:
-        if mode == 'nccl':
+        if mode == 'p2p' and world > 1:
+            merges, stats = cl.run_sharded_p2p(0.0, 0, rank, world, mbx.ptrs, mbx.next_base(len(a)))
+        elif mode == 'nccl' or world == 1:
             merges, stats = cl.run_sharded_nccl(0.0, 0, rank, world, nid)
         else:
             merges, stats = cl.run_sharded(0.0, 0, rank, world, ex)
@@ -48,5 +53,8 @@ hours = rec.frames.shape[0] / 100.0 / 3600.0
 print(mode, 'rank %d/%d: segments %d merges %d speakers %d  wall %.1f ms (fill %.1f ms, merge kernels %.1f ms)  %.2f audio-h/s  sha %s'
       % (rank, world, len(a), len(merges), len(a) - len(merges), dt * 1e3, prof['score'][0], prof['merge'][0],
          hours / dt, hashlib.sha256(merges.tobytes()).hexdigest()[:12]), flush=True)
+if mbx is not None:
+    dist.barrier()
+    mbx.close()
 if world > 1:
     dist.destroy_process_group()
