@@ -150,18 +150,20 @@ class Detector(object):
     def _gw_replay(self, feat, line, a, b, recs, outf, segf):
         st = self.stats
         start = 0
-        for r in recs:
-            self.windows_visited += 1
-            if r['ninf'] > 0:
-                self._gw_inf_lines(feat, a, r)
-            maxd = float(r['maxd']) if r['ncand'] >= 0 else NEG_INIT
-            st.window(maxd)
-            if r['positive']:
-                maxd = float(r['maxd_fine'])
-                maxi = float(r['maxi_fine'])
-                start = float(r['start'])
+        # plain Python lists: item access on a structured array costs microseconds per field
+        ninf, ncand, pos = recs['ninf'].tolist(), recs['ncand'].tolist(), recs['positive'].tolist()
+        maxds, maxd_f, maxi_f, starts = (recs['maxd'].tolist(), recs['maxd_fine'].tolist(),
+                                         recs['maxi_fine'].tolist(), recs['start'].tolist())
+        self.windows_visited += len(ninf)
+        for i in range(len(ninf)):
+            if ninf[i] > 0:
+                self._gw_inf_lines(feat, a, recs[i])
+            st.window(maxds[i] if ncand[i] >= 0 else NEG_INIT)
+            if pos[i]:
+                maxi = maxi_f[i]
+                start = starts[i]
                 self.writer.write(line, start, start + maxi, line.start, 'spk_turn', outf, segf)
-                st.detected(maxd)
+                st.detected(maxd_f[i])
                 start += maxi
         end = (line.end - line.start) * self.rate                 # CD:287
         self.writer.write(line, start, end, line.start, 'spk_turn', outf, segf)
