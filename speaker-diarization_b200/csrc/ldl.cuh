@@ -307,6 +307,148 @@ __device__ __forceinline__ double ldl_logdet(double (&a)[Grid<D>::NSLOT], LdlScr
     return bad ? __longlong_as_double(0x7ff8000000000000LL) : s;
 }
 
+// ---- factorisation fused with the inverse of the factor (KL2) -------------
+// KL2 needs diag(M^-1) = diag(L^-T D^-1 L^-1): diag(M^-1)_k = q_k + sum_{r > k} X_rk^2 q_r with
+// X = L^-1 (unit lower triangular) and q = 1 / pivot.  X is accumulated DURING the elimination:
+// step C applies X_r,: -= l_rC X_C,: to the rows r > C (X_rC starts as -l_rC), i.e. to the
+// entries (r, k) with r > C > k - exactly the register slots the elimination has FINISHED with
+// (column k < C of M is done).  So the same 30 slots per lane hold M's live part (k > C) and X's
+// grown part (k < C), every step updates all of them with one FMA each, and the inverse costs no
+// extra dependent chain: row C of X travels through the second pair of strips next to column C.
+// On entry of step C the lane holds the pivot, vr[ri] = M_rC of its rows and cf[kj] = M_kC of its
+// columns k > C or X_Ck of its columns k < C.
+template <int D, int C>
+struct LdlInvStep {
+    using G = Grid<D>;
+    static __device__ __forceinline__ void run(double (&a)[G::NSLOT], LdlScratch& w, int lane, int i, int j,
+                                               const double (&vr)[G::NRI], const double (&cf)[G::NKJ],
+                                               double piv, double q,
+                                               double& p0, double& p1, bool& bad, double* pinv) {
+        constexpr int kjb = C / G::PC, jC = C % G::PC;                // local column / owner lanes of column C
+        constexpr int rib = C / G::PR, iC = C % G::PR;                // local row that holds row C
+        constexpr int kn = (C + 1) / G::PC, jn = (C + 1) % G::PC;     // ... of column C + 1
+        constexpr int rn = (C + 1) / G::PR, in = (C + 1) % G::PR;     // ... of row C + 1
+        double* vn = w.v[(C + 1) & 1];
+        double* xn = (C + 1) & 1 ? w.s1 : w.s0;                       // X row strips (free after form_matrix)
+        bad |= !(piv > 0.0);
+        if ((C & 31) == lane) { if (C < 32) p0 = piv; else p1 = piv; }
+        st_shared_if(lane == 0, pinv + C, q);
+        // l_rC of the lane's rows r > C (0 for r <= C: those slots are finished and must not move)
+        double lr[G::NRI];
+#pragma unroll
+        for (int ri = rib; ri < G::NRI; ++ri) {
+            const double l = vr[ri] * q;
+            lr[ri] = (ri > rib || i > iC) ? l : 0.0;
+        }
+        // one update per slot (kj, ri), ri >= max(2 kj, rib):
+        //   k > C : M_rk -= l_rC M_kC       k < C : X_rk -= l_rC X_Ck       k == C : X_rC = -l_rC
+        auto update = [&](int kj, int ri) {
+            const int sl = G::slot(kj, ri);
+            const double t = fma(-lr[ri], cf[kj], a[sl]);
+            if (kj == kjb) a[sl] = (j == jC && (ri > rib || i > iC)) ? -lr[ri] : t;
+            else a[sl] = t;
+        };
+        double nvr[G::NRI], ncf[G::NKJ], npiv = 1.0, nq = 1.0;
+        if (C + 1 < D) {
+            // first what the next step needs: local column kn (column C + 1 of M) and local row rn
+            // (row C + 1 of X)
+#pragma unroll
+            for (int ri = (rib > G::ri_first(kn) ? rib : G::ri_first(kn)); ri < G::NRI; ++ri) update(kn, ri);
+#pragma unroll
+            for (int kj = 0; kj < G::NKJ; ++kj)
+                if (kj != kn && rn >= G::ri_first(kj) && rn >= rib) update(kj, rn);
+#pragma unroll
+            for (int ri = (rib > G::ri_first(kn) ? rib : G::ri_first(kn)); ri < G::NRI; ++ri) {
+                const int r = i + G::PR * ri;
+                st_shared_if(j == jn && r > C && r < D, vn + r, a[G::slot(kn, ri)]);
+            }
+#pragma unroll
+            for (int kj = 0; kj <= kn; ++kj) {
+                if (rn < G::ri_first(kj)) continue;
+                const int k = j + G::PC * kj;
+                st_shared_if(i == in && k <= C, xn + k, a[G::slot(kj, rn)]);
+            }
+            __syncwarp();
+            constexpr int ri_n = (C + 1) / G::PR;
+            npiv = vn[C + 1];
+#pragma unroll
+            for (int ri = ri_n; ri < G::NRI; ++ri) nvr[ri] = vn[i + G::PR * ri];
+#pragma unroll
+            for (int kj = 0; kj < G::NKJ; ++kj) {
+                const int k = j + G::PC * kj;
+                // columns right of C + 1: M_k,C+1; left of it: X_C+1,k; the lane's own column C + 1: unused
+                const double* src = (kj > kn || (kj == kn && j > jn)) ? vn : xn;
+                ncf[kj] = src[k];
+            }
+            nq = fast_rcp(npiv);
+            // then the rest
+#pragma unroll
+            for (int kj = 0; kj < G::NKJ; ++kj) {
+                if (kj == kn) continue;
+#pragma unroll
+                for (int ri = (rib > G::ri_first(kj) ? rib : G::ri_first(kj)); ri < G::NRI; ++ri)
+                    if (ri != rn) update(kj, ri);
+            }
+        }
+        LdlInvStep<D, C + 1>::run(a, w, lane, i, j, nvr, ncf, npiv, nq, p0, p1, bad, pinv);
+    }
+};
+template <int D>
+struct LdlInvStep<D, D> {
+    using G = Grid<D>;
+    static __device__ __forceinline__ void run(double (&)[G::NSLOT], LdlScratch&, int, int, int,
+                                               const double (&)[G::NRI], const double (&)[G::NKJ], double, double,
+                                               double&, double&, bool&, double*) {}
+};
+
+// ln|M| and diag(M^-1) (into dinv[0..D-1], scaled by `scale`; NaN when a pivot is not > 0).
+// pinv: VS doubles of shared memory.  Uses w.s0 / w.s1 as strips: form_matrix's vectors are gone after.
+template <int D>
+__device__ __forceinline__ double ldl_logdet_inv(double (&a)[Grid<D>::NSLOT], LdlScratch& w, int lane,
+                                                 double* pinv, double scale, double* dinv) {
+    using G = Grid<D>;
+    double p0 = 1.0, p1 = 1.0;
+    bool bad = false;
+    const int i = lane >> 3, j = lane & 7;
+    __syncwarp();
+#pragma unroll
+    for (int ri = 0; ri < G::NRI; ++ri)    // prologue: publish column 0 and read it back (row 0 of X is empty)
+        st_shared_if(j == 0 && i + G::PR * ri < D, w.v[0] + i + G::PR * ri, a[G::slot(0, ri)]);
+    __syncwarp();
+    double vr[G::NRI], cf[G::NKJ];
+    const double piv = w.v[0][0];
+#pragma unroll
+    for (int ri = 0; ri < G::NRI; ++ri) vr[ri] = w.v[0][i + G::PR * ri];
+#pragma unroll
+    for (int kj = 0; kj < G::NKJ; ++kj) cf[kj] = w.v[0][j + G::PC * kj];
+    LdlInvStep<D, 0>::run(a, w, lane, i, j, vr, cf, piv, fast_rcp(piv), p0, p1, bad, pinv);
+    double s = log(p0);
+    if (D > 32) s += log(p1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncwarp();                                              // pinv complete
+    // diag(M^-1)_k = q_k + sum_{r > k} X_rk^2 q_r: per lane over its rows, then over the four lanes of a column
+    double qr[G::NRI];
+#pragma unroll
+    for (int ri = 0; ri < G::NRI; ++ri) { const int r = i + G::PR * ri; qr[ri] = r < D ? pinv[r] : 0.0; }
+#pragma unroll
+    for (int kj = 0; kj < G::NKJ; ++kj) {
+        const int k = j + G::PC * kj;
+        double acc = 0.0;
+#pragma unroll
+        for (int ri = G::ri_first(kj); ri < G::NRI; ++ri) {
+            const int r = i + G::PR * ri;
+            const double x = (r > k && r < D) ? a[G::slot(kj, ri)] : 0.0;
+            acc = fma(x * x, qr[ri], acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (i == 0 && k < D) dinv[k] = bad ? __longlong_as_double(0x7ff8000000000000LL) : (acc + pinv[k]) * scale;
+    }
+    __syncwarp();
+    return bad ? __longlong_as_double(0x7ff8000000000000LL) : s;
+}
+
 // ln|S| of the reference from ln|M|:  S = M / (n - 1).  Also applies the range
 // mapping of np.log(det(S)): a determinant that under/overflows
 // fp64 makes the reference see -inf / +inf.

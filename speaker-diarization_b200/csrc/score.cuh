@@ -204,15 +204,9 @@ __device__ __forceinline__ void kl2_side_one(const Src& gsrc, Scr& k, double* dS
         const double s = k.w.s0[j];
         dS[j] = (src(L39::pos_diag(j)) - s * s / n) * rn1;
     }
-    __syncwarp();                       // the record buffer becomes the factor store
-    const double lm = ldl_logdet<D39, true>(a, k.w, lane, k.Lsm, k.pinv);
-    double ga, gb;
-    inv_diag<D39>(k.Lsm, k.pinv, lane, ga, gb);
-    const bool bad = !(lm == lm);
-    if (lane < InvCols<D39>::NL) {
-        dP[lane] = bad ? d_nan() : ga * (n - 1.0);
-        dP[D39 - 1 - lane] = bad ? d_nan() : gb * (n - 1.0);
-    }
+    __syncwarp();
+    // factorisation with the inverse of the factor accumulated in the finished register slots
+    ldl_logdet_inv<D39>(a, k.w, lane, k.pinv, n - 1.0, dP);
     __syncwarp();
 }
 
