@@ -54,7 +54,7 @@ SEQUENTIAL = bool(os.environ.get('SPKDIAR_BENCH_SEQUENTIAL'))      # one search 
 # algorithmic work per unit (restated in DESIGN.md)
 FLOP_LOGDET = 22893.0               # form 39x39 from prefix differences + factorise
 FLOP_KL2 = 85332.0
-BYTES_STATS_PER_FRAME = 2 * 156 + 6560
+BYTES_STATS_PER_FRAME = 156 + 6560          # frames read once, one prefix record written per frame
 
 
 def make_recording(rank):
