@@ -463,6 +463,13 @@ def main():
         rl_all[k] = {'bound': spec['bound'], 'achieved': ach, 'peak': spec['peak'], 'unit': spec['unit'],
                      'frac': ach / spec['peak'], 'peak_source': spec['peak_source'],
                      'ms_per_step': ms_k / steps, 'launches_per_step': n_k / steps, 'traffic': None}
+    try:                                    # DRAM traffic per launch from this round's ncu captures
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+        for k in rl_all:
+            if k in traffic:
+                rl_all[k]['traffic'] = traffic[k]['bytes_per_launch']
+    except (OSError, ValueError, KeyError):
+        pass
     dominant = max(rl_all, key=lambda k: rl_all[k]['ms_per_step'])
     roofline = dict(rl_all[dominant], kernel=dominant)
 
