@@ -297,10 +297,19 @@ def run_other_workload(args):
             items.append(('c4_%d' % k, synth.one_line_recipe('/syn/c4_%d.wav' % k, r), r.frames))
         hours_per_step, scaling = world * args.files * (60000 / RATE / 3600.0), 'weak'
         desc = ('config4: %d ten-minute recordings per GPU, spk-diarization2 flags (gw BIC change detection + CL1), '
-                'host frames through the drop-in API' % args.files)
+                'host frames through the drop-in API, %s' % (args.files, 'device batches of %d recordings (packed '
+                'statistics, one growing-window launch with one CTA per recording, one clustering launch)' % args.batch
+                if args.batch > 0 else 'one recording at a time'))
+        pinned = [torch.from_numpy(frames).pin_memory() for _, _, frames in items]
 
         def step():
             out = None
+            if args.batch > 0:
+                for b0 in range(0, len(items), args.batch):
+                    part = [(items[k][1], (pinned[k].data_ptr(), pinned[k].shape[0]))
+                            for k in range(b0, min(b0 + args.batch, len(items)))]
+                    out = corpus.diarize_batch(ctx, part, RATE)[-1]
+                return out
             for name, lines, frames in items:
                 f = ctx.upload(frames)
                 try:
@@ -347,6 +356,7 @@ def main():
                     help='config2 is the headline (BASELINE.json configs[1]); the others print their own line')
     ap.add_argument('--segments', type=int, default=8000, help='config5: segments of the long recording')
     ap.add_argument('--files', type=int, default=16, help='config4: recordings per GPU')
+    ap.add_argument('--batch', type=int, default=0, help='config4: recordings per device batch (0: one at a time)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

@@ -95,6 +95,15 @@ int  spkdiar_features_upload(spkdiar_ctx* ctx, const float* frames, int64_t n,
  * outlive the handle) */
 int  spkdiar_features_adopt(spkdiar_ctx* ctx, const float* dev_frames, int64_t n,
                             int32_t dim, spkdiar_feat** out);
+/* A BATCH of recordings in one handle (BASELINE config 4: spk-diarization2.py over a corpus,
+ * lines 122-128 once per media file).  Recording r is copied to the packed frame rows
+ * [base_out[r], base_out[r] + n[r]) (base_out[r] is a multiple of 128) and its statistics
+ * restart there, so every result over a packed recording is bit-identical to the result over
+ * the same recording uploaded alone; frame positions passed to later calls on this handle
+ * (chains, segments, windows) are PACKED positions.  One spkdiar_gw_run over the chains of all
+ * recordings and one spkdiar_cluster_batch then process the whole batch in two launches. */
+int  spkdiar_features_upload_batch(spkdiar_ctx* ctx, const float* const* frames, const int64_t* n,
+                                   int32_t nrec, int32_t dim, spkdiar_feat** out, int64_t* base_out);
 /* (re)build the prefix statistics; upload/adopt already call it once */
 int  spkdiar_stats_build(spkdiar_feat* f);
 int  spkdiar_features_free(spkdiar_feat* f);
@@ -254,6 +263,16 @@ int  spkdiar_cluster_run_sharded_p2p(spkdiar_clus* c, double threshold, int32_t 
                                      int32_t rank, int32_t nranks, void* const* mailboxes,
                                      uint64_t seq_base, spkdiar_merge* out, int64_t cap,
                                      int64_t* nmerges, double* stats4);
+/* Many SMALL clustering problems in one launch (one CTA per problem, no grid barrier):
+ * problem p clusters the segments first[p] .. first[p + 1] of (seg_a, seg_b) exactly as
+ * spkdiar_cluster_create + spkdiar_cluster_run would (same merges, distances, statistics,
+ * bit for bit).  out has first[nprob] slots, the merges of problem p start at out[first[p]];
+ * nmerges[p] of them are valid; stats4 (may be NULL) holds 4 doubles per problem.  Problems
+ * larger than 4096 segments are refused (SPKDIAR_E_UNSUPPORTED): use the resident engine. */
+int  spkdiar_cluster_batch(spkdiar_feat* f, int32_t nprob, const int64_t* first,
+                           const int64_t* seg_a, const int64_t* seg_b, int metric, double lambda,
+                           double threshold, int32_t max_spk, int32_t variant,
+                           spkdiar_merge* out, int64_t* nmerges, double* stats4);
 int  spkdiar_cluster_free(spkdiar_clus* c);
 /* test hook: copy the current pair matrix (nseg x nseg, row-major, entries of
  * dead rows / columns undefined) and the alive flags to the host */

@@ -33,6 +33,7 @@ SYMBOLS = (
     'spkdiar_cluster_run_sharded_p2p', 'spkdiar_mailbox_create', 'spkdiar_mailbox_open',
     'spkdiar_mailbox_close', 'spkdiar_mailbox_free',
     'spkdiar_cluster_free', 'spkdiar_cluster_matrix',
+    'spkdiar_features_upload_batch', 'spkdiar_cluster_batch',
 )
 
 
@@ -117,6 +118,8 @@ def load_library(path=None):
         'spkdiar_mailbox_free': (C.c_int, [vp, vp]),
         'spkdiar_cluster_free': (C.c_int, [vp]),
         'spkdiar_cluster_matrix': (C.c_int, [vp, pdbl, C.POINTER(C.c_uint8)]),
+        'spkdiar_features_upload_batch': (C.c_int, [vp, C.POINTER(vp), pi64, i32, i32, C.POINTER(vp), pi64]),
+        'spkdiar_cluster_batch': (C.c_int, [vp, i32, pi64, pi64, pi64, C.c_int, dbl, dbl, i32, i32, vp, pi64, pdbl]),
     }
     for name, (res, args) in proto.items():
         fn = getattr(lib, name)
@@ -201,6 +204,31 @@ class Context(object):
         h = C.c_void_p()
         self._check(self.lib.spkdiar_features_upload(self.h, C.c_void_p(host_ptr), n, dim, C.byref(h)))
         return Features(self, h, n)
+
+    def upload_batch(self, matrices):
+        """A batch of recordings -> FeaturePack (one packed handle, statistics restarting per
+        recording).  ``matrices``: (n_r, 39) float32 arrays, or (host pointer, n_r) pairs
+        (e.g. pinned torch memory)."""
+        keep, ptrs, ns = [], [], []
+        for m in matrices:
+            if isinstance(m, tuple):
+                ptrs.append(int(m[0]))
+                ns.append(int(m[1]))
+            else:
+                m = np.ascontiguousarray(m, dtype=np.float32)
+                if m.ndim != 2 or m.shape[1] != DIM:
+                    raise SpkdiarError(-5, 'feature dimension %r: the kernels are specialised for %d' % (m.shape, DIM))
+                keep.append(m)
+                ptrs.append(m.ctypes.data)
+                ns.append(m.shape[0])
+        nrec = len(ptrs)
+        arr = (C.c_void_p * max(nrec, 1))(*[C.c_void_p(p) for p in ptrs])
+        n = np.array(ns, dtype=np.int64)
+        base = np.zeros(max(nrec, 1), dtype=np.int64)
+        h = C.c_void_p()
+        self._check(self.lib.spkdiar_features_upload_batch(self.h, arr, _p(n, C.c_int64), nrec, DIM,
+                                                           C.byref(h), _p(base, C.c_int64)))
+        return FeaturePack(self, h, base[:nrec].tolist(), ns)
 
     def adopt(self, dev_ptr, n, dim=DIM):
         """Features over a matrix already in device memory (not copied)."""
@@ -331,6 +359,100 @@ class Features(object):
             self.h, _p(seg_a, C.c_int64), _p(seg_b, C.c_int64), seg_a.shape[0], int(metric),
             float(lambdac), C.byref(h)))
         return Clusters(self, h, seg_a.shape[0])
+
+
+class FeaturePack(Features):
+    """A batch of recordings in one handle (``spkdiar_features_upload_batch``).  Positions on
+    the pack itself are packed frame rows; ``view(r)`` is recording r with its own positions."""
+
+    def __init__(self, ctx, handle, base, n):
+        Features.__init__(self, ctx, handle, (base[-1] + (n[-1] // 128 + 1) * 128) if n else 0)
+        self.base = list(base)
+        self.lengths = list(n)
+
+    def __len__(self):
+        return len(self.base)
+
+    def view(self, r):
+        return FeatureView(self, r)
+
+    def gw_run_batch(self, chains, rate, winsize, winstep, deltaws, threshold, lambdac, metric):
+        """``chains[r]``: list of (a, b) frame ranges of recording r (its recipe lines).  All
+        chains of all recordings run in ONE launch (one CTA per chain when there are at least
+        as many chains as SMs).  -> per recording (records, win_first) exactly as
+        ``view(r).gw_run`` returns them."""
+        seg_a, seg_b, owner = [], [], [0]
+        for r, ch in enumerate(chains):
+            for a, b in ch:
+                seg_a.append(self.base[r] + int(a))
+                seg_b.append(self.base[r] + int(b))
+            owner.append(len(seg_a))
+        win, first = self.gw_run(seg_a, seg_b, rate, winsize, winstep, deltaws, threshold, lambdac, metric)
+        out = []
+        for r in range(len(chains)):
+            c0, c1 = owner[r], owner[r + 1]
+            recs = win[int(first[c0]):int(first[c1])].copy()
+            recs['chain'] -= c0
+            out.append((recs, first[c0:c1 + 1] - first[c0]))
+        return out
+
+    def cluster_batch(self, problems, metric, lambdac=1.3, threshold=0.0, max_spk=0, variant=1):
+        """``problems[r]``: list of (a, b) frame ranges of recording r, the initial clusters of
+        one ``spk_cluster_hi`` run.  One launch, one CTA per problem.  -> per problem
+        (merges, stats[4]) exactly as ``view(r).cluster(...).run(...)`` returns them."""
+        first = np.zeros(len(problems) + 1, dtype=np.int64)
+        seg_a, seg_b = [], []
+        for r, segs in enumerate(problems):
+            for a, b in segs:
+                seg_a.append(self.base[r] + int(a))
+                seg_b.append(self.base[r] + int(b))
+            first[r + 1] = len(seg_a)
+        seg_a, seg_b = _i64(seg_a), _i64(seg_b)
+        out = np.zeros(max(len(seg_a), 1), dtype=MERGE_DTYPE)
+        nm = np.zeros(max(len(problems), 1), dtype=np.int64)
+        stats = np.zeros((max(len(problems), 1), 4))
+        self.ctx._check(self.ctx.lib.spkdiar_cluster_batch(
+            self.h, len(problems), _p(first, C.c_int64), _p(seg_a, C.c_int64), _p(seg_b, C.c_int64),
+            int(metric), float(lambdac), float(threshold), int(max_spk), int(variant),
+            out.ctypes.data_as(C.c_void_p), _p(nm, C.c_int64), _p(stats, C.c_double)))
+        return [(out[int(first[r]):int(first[r]) + int(nm[r])], stats[r]) for r in range(len(problems))]
+
+
+class FeatureView(object):
+    """Recording r of a FeaturePack with the interface of ``Features`` (positions are the
+    recording's own frame indices).  Closing a view does nothing: the pack owns the memory."""
+
+    def __init__(self, pack, r):
+        self.pack = pack
+        self.ctx = pack.ctx
+        self.r = int(r)
+        self.off = int(pack.base[r])
+        self.n = int(pack.lengths[r])
+
+    def close(self):
+        pass
+
+    def _sh(self, a):
+        return _i64(a) + self.off
+
+    def stats_window(self, a, b):
+        return self.pack.stats_window(int(a) + self.off, int(b) + self.off)
+
+    def score_windows(self, a, m, b, metric, lambdac=1.3, terms=False):
+        return self.pack.score_windows(self._sh(a), self._sh(m), self._sh(b), metric, lambdac, terms)
+
+    def score_sets(self, sets1, sets2, metric, lambdac=1.3, terms=False):
+        sh = lambda sets: [[(a + self.off, b + self.off) for a, b in s] for s in sets]
+        return self.pack.score_sets(sh(sets1), sh(sets2), metric, lambdac, terms)
+
+    def gw_run(self, seg_a, seg_b, *args, **kw):
+        return self.pack.gw_run(self._sh(seg_a), self._sh(seg_b), *args, **kw)
+
+    def gw_run_multi(self, seg_a, seg_b, runs, max_groups=0):
+        return self.pack.gw_run_multi(self._sh(seg_a), self._sh(seg_b), runs, max_groups)
+
+    def cluster(self, seg_a, seg_b, metric, lambdac=1.3):
+        return self.pack.cluster(self._sh(seg_a), self._sh(seg_b), metric, lambdac)
 
 
 class Clusters(object):

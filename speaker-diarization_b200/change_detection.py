@@ -133,6 +133,33 @@ class Detector(object):
         return a, max(a, b)
 
     # ---- growing window ------------------------------------------------------
+    def gw_chains(self, recipe, loader):
+        """The chains ``detect_changes`` will hand to the device, without running them:
+        [(feat, [(a, b), ...])] per run of lines of one wav (the walk of CD:360-374).  The
+        corpus driver uses it to put the chains of a whole batch of recordings into one launch
+        and ``prefetch`` the records."""
+        groups = []
+        this_wav = this_lna = ''
+        feat = None
+        chains = []
+        for line in recipe:
+            if line.audio != this_wav:
+                if chains:
+                    groups.append((feat, chains))
+                    chains = []
+                this_wav = line.audio
+                feat = loader(line)
+            if line.lna != this_lna:
+                this_lna = line.lna
+                chains.append(self._bounds(line, feat.n))
+        if chains:
+            groups.append((feat, chains))
+        return groups
+
+    def prefetch(self, feat, chains, result):
+        """``result`` = what ``feat.gw_run`` would return for these chains."""
+        self._prefetch[(id(feat), tuple(c[0] for c in chains), tuple(c[1] for c in chains))] = result
+
     def _gw_device(self, feat, chains, outf, segf):
         """All chains of one wav in one persistent-kernel launch, then replay."""
         if not chains:

@@ -61,6 +61,17 @@ class Clusterer(object):
         self.engine = engine
         self._own_ctx = ctx is None
         self.ctx = ctx if ctx is not None else _abi.Context(device)
+        self._prefetch = {}
+
+    def initial_segments(self, recipe, n):
+        """The frame ranges of the initial clusters of a hierarchical run over ``recipe``
+        (CL1:282-283 + CL1:47), without running it."""
+        return [self._range((line.start * self.rate, line.end * self.rate), n) for line in recipe]
+
+    def prefetch(self, feat, segments, result):
+        """``result`` = what ``feat.cluster(segments).run(...)`` would return (the corpus driver
+        clusters a whole batch of recordings in one launch)."""
+        self._prefetch[(id(feat), tuple(segments))] = result
 
     def close(self):
         if self._own_ctx and self.ctx is not None:
@@ -133,8 +144,12 @@ class Clusterer(object):
     def _merge_sequence_device(self, feat):
         n = feat.n
         seg = [self._range(s[0], n) for s in self.speakers]
-        with feat.cluster([r[0] for r in seg], [r[1] for r in seg], self.metric, self.lambdac) as cl:
-            merges, stats = cl.run(self.threshold, self.max_spk, self.variant)
+        got = self._prefetch.pop((id(feat), tuple(seg)), None)
+        if got is not None:
+            merges, stats = got
+        else:
+            with feat.cluster([r[0] for r in seg], [r[1] for r in seg], self.metric, self.lambdac) as cl:
+                merges, stats = cl.run(self.threshold, self.max_spk, self.variant)
         if self.variant == 1:
             self.max_dist, self.min_dist = self._stat(stats[0], 0), self._stat(stats[1], MAXINT)
             self.max_det_dist = self._stat(stats[2], 0)

@@ -51,8 +51,64 @@ def diarize_recording(ctx, recipe_lines, frames_loader, frame_rate=125, threshol
     return seg.getvalue(), out.getvalue(), summary
 
 
+def diarize_batch(ctx, batch, frame_rate=125, threshold=0.0):
+    """A batch of recordings through change detection + clustering with the device work of the
+    WHOLE batch in four launches: packed upload + statistics, one growing-window launch over the
+    chains of all recordings (one CTA per chain), one clustering launch (one CTA per recording).
+    ``batch``: list of (recipe_lines, frames).  Returns [(segmentation recipe text, clustered
+    recipe text, summary)] - byte-identical to ``diarize_recording`` on each item (the packed
+    statistics restart per recording; the host replay is the same code)."""
+    from . import change_detection as pcd, clustering as pcl
+    pack = ctx.upload_batch([frames() if callable(frames) else frames for _, frames in batch])
+    try:
+        views = [pack.view(r) for r in range(len(batch))]
+        parsed = [recipe_mod.parse(lines) for lines, _ in batch]
+        dets = [pcd.Detector(frame_rate, threshold=threshold, ctx=ctx, **D2_CHANGE) for _ in batch]
+        # ---- change detection: every chain of every recording in one launch ----
+        groups = [det.gw_chains(rec, lambda l, v=v: v) for det, rec, v in zip(dets, parsed, views)]
+        flat = [(r, k) for r, grp in enumerate(groups) for k in range(len(grp))]
+        chains = [[] for _ in batch]
+        for r, k in flat:
+            chains[r].extend(groups[r][k][1])
+        d0 = dets[0]
+        results = pack.gw_run_batch(chains, d0.rate, d0.winsize, d0.winstep, d0.deltaws, d0.threshold,
+                                    d0.lambdac, d0.metric)
+        seg_lines = []
+        for r, (det, rec, v) in enumerate(zip(dets, parsed, views)):
+            win, first = results[r]
+            c0 = 0
+            for feat, ch in groups[r]:                       # usually one group: one wav per recipe
+                lo, hi = int(first[c0]), int(first[c0 + len(ch)])
+                sub = win[lo:hi].copy()
+                sub['chain'] -= c0
+                det.prefetch(feat, ch, (sub, first[c0:c0 + len(ch) + 1] - first[c0]))
+                c0 += len(ch)
+            seg = io.StringIO()
+            det.detect_changes(rec, seg, loader=lambda l, v=v: v)
+            seg_lines.append(seg.getvalue().splitlines(True))
+        # ---- clustering: one problem per recording, one launch ----
+        cls = [pcl.Clusterer(frame_rate, variant=1, threshold=threshold, ctx=ctx, **D2_CLUSTER) for _ in batch]
+        seg_parsed = [recipe_mod.parse(lines) for lines in seg_lines]
+        problems = [cl.initial_segments(rec, v.n) for cl, rec, v in zip(cls, seg_parsed, views)]
+        live = [r for r, p in enumerate(problems) if p]
+        merged = pack.cluster_batch([problems[r] for r in live], cls[0].metric, cls[0].lambdac,
+                                    threshold, 0, 1) if live else []
+        out = []
+        for r, (cl, rec, v) in enumerate(zip(cls, seg_parsed, views)):
+            if r in live:
+                cl.prefetch(v, problems[r], merged[live.index(r)])
+            clu = io.StringIO()
+            cl.process_recipe(rec, clu, loader=lambda l, v=v: v)
+            summary = dict(turns=len(seg_lines[r]), speakers=len(cl.speakers), windows=dets[r].windows_visited,
+                           merges=len(cl.merges))
+            out.append((''.join(seg_lines[r]), clu.getvalue(), summary))
+        return out
+    finally:
+        pack.close()
+
+
 def run_corpus(items, rank=0, world=1, device=None, outdir=None, frame_rate=125, runner=None,
-               gather=None):
+               gather=None, batch=0):
     """Diarize the items this rank owns.
 
     ``items``  list of (name, recipe_lines, frames) with ``frames`` a float32
@@ -61,6 +117,8 @@ def run_corpus(items, rank=0, world=1, device=None, outdir=None, frame_rate=125,
                the default uploads the frames and calls ``diarize_recording``);
     ``gather`` ``gather(obj) -> list of every rank's obj`` (e.g. built on
                ``torch.distributed.all_gather_object``); None = single process.
+    ``batch``  recordings per device batch (``diarize_batch``: the device work of the whole
+               batch in four launches); 0 = one recording at a time.
 
     Returns {name: summary} for the WHOLE corpus on every rank (after the
     gather) - results do not depend on the number of ranks.
@@ -80,9 +138,17 @@ def run_corpus(items, rank=0, world=1, device=None, outdir=None, frame_rate=125,
                     return diarize_recording(ctx, lines, lambda l: feat, frame_rate)
                 finally:
                     feat.close()
-        for k in mine:
-            name, lines, frames = items[k]
-            seg, clu, summary = runner(name, lines, frames)
+        results = []
+        if batch > 0 and ctx is not None:
+            for b0 in range(0, len(mine), batch):
+                part = [items[k] for k in mine[b0:b0 + batch]]
+                got = diarize_batch(ctx, [(lines, frames) for _, lines, frames in part], frame_rate)
+                results.extend((name,) + g for (name, _, _), g in zip(part, got))
+        else:
+            for k in mine:
+                name, lines, frames = items[k]
+                results.append((name,) + tuple(runner(name, lines, frames)))
+        for name, seg, clu, summary in results:
             if outdir is not None:
                 os.makedirs(outdir, exist_ok=True)
                 with open(op.join(outdir, name + '.spkc.recipe'), 'w') as f:

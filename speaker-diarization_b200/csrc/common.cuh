@@ -54,6 +54,10 @@ struct spkdiar_feat {
     double* tile = nullptr;       // per-block totals
     double2* chunk = nullptr;     // per-chunk double-double totals of the block scan
     int64_t ntiles = 0;
+    // packed batch of recordings (spkdiar_features_upload_batch): nrec > 0, n = packed rows
+    int32_t nrec = 0;
+    void* tab = nullptr;          // device RecTab[nrec]
+    int64_t max_tiles = 0;        // blocks of the longest recording
 };
 
 namespace spk {

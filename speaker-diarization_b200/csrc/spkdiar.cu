@@ -20,6 +20,7 @@
 #include "score.cuh"
 #include "gw.cuh"
 #include "cluster.cuh"
+#include "cluster_batch.cuh"
 
 using namespace spk;
 
@@ -88,6 +89,7 @@ int spkdiar_create(int device, void* stream, spkdiar_ctx** out) {
     if ((e = cudaFuncSetAttribute(pair_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM)) != cudaSuccess) goto fail;
     if ((e = gw_configure()) != cudaSuccess) goto fail;
     if ((e = cluster_configure()) != cudaSuccess) goto fail;
+    if ((e = cluster_batch_configure()) != cudaSuccess) goto fail;
     *out = c;
     return SPKDIAR_OK;
 fail:
@@ -133,7 +135,7 @@ int spkdiar_profile_read(const spkdiar_ctx* c, double* ms, int64_t* launches) {
 
 // ---- features + K1 ------------------------------------------------------------------------
 
-static int feat_alloc(spkdiar_ctx* c, int64_t n, int32_t dim, spkdiar_feat** out) {
+static int feat_alloc(spkdiar_ctx* c, int64_t n, int32_t dim, spkdiar_feat** out, int32_t nrec = 0) {
     if (!c || !out) return SPKDIAR_E_ARG;
     *out = nullptr;
     if (n < 0) return set_err(c, SPKDIAR_E_ARG, "negative frame count %lld", (long long)n);
@@ -149,8 +151,8 @@ static int feat_alloc(spkdiar_ctx* c, int64_t n, int32_t dim, spkdiar_feat** out
     cudaError_t e;
     if ((e = pool_alloc(c, (size_t)(n + 1) * REC * sizeof(double), (void**)&f->P)) != cudaSuccess ||
         (e = pool_alloc(c, (size_t)(f->ntiles + 1) * REC * sizeof(double2), (void**)&f->C)) != cudaSuccess ||
-        (e = pool_alloc(c, K1_XS * sizeof(double), (void**)&f->shift)) != cudaSuccess ||
-        (e = pool_alloc(c, (size_t)K1_CHUNKS * REC * sizeof(double2), (void**)&f->chunk)) != cudaSuccess ||
+        (e = pool_alloc(c, (size_t)std::max(nrec, 1) * K1_XS * sizeof(double), (void**)&f->shift)) != cudaSuccess ||
+        (e = pool_alloc(c, (size_t)std::max(nrec, 1) * K1_CHUNKS * REC * sizeof(double2), (void**)&f->chunk)) != cudaSuccess ||
         (e = pool_alloc(c, (size_t)std::max<int64_t>(f->ntiles, 1) * REC * sizeof(double), (void**)&f->tile)) != cudaSuccess) {
         pool_free(c, f->P);
         pool_free(c, f->C);
@@ -170,7 +172,16 @@ int spkdiar_stats_build(spkdiar_feat* f) {
     SPK_CUDA(c, cudaSetDevice(c->device));
     {
         Prof p(c, SPKDIAR_PROF_STATS);
-        if (f->n == 0) {
+        if (f->nrec > 0) {
+            const RecTab* tab = (const RecTab*)f->tab;
+            const dim3 sg((K1_CHUNKS * REC + 127) / 128, (unsigned)f->nrec);
+            k1_shift_batch<<<(unsigned)f->nrec, 1024, 0, c->stream>>>(f->x, tab, f->shift);
+            k1_tile_write_batch<<<dim3((unsigned)f->max_tiles, (unsigned)f->nrec), K1_THREADS, 0, c->stream>>>(
+                f->x, tab, f->shift, f->tile, f->P);
+            k1_chunk_sums_batch<<<sg, 128, 0, c->stream>>>(f->tile, tab, f->chunk);
+            k1_chunk_scan_batch<<<sg, 128, 0, c->stream>>>(f->tile, tab, f->chunk, f->C);
+            c->launches += 4;
+        } else if (f->n == 0) {
             SPK_CUDA(c, cudaMemsetAsync(f->P, 0, REC * sizeof(double), c->stream));
             SPK_CUDA(c, cudaMemsetAsync(f->C, 0, REC * sizeof(double2), c->stream));
         } else {
@@ -211,6 +222,52 @@ int spkdiar_features_upload(spkdiar_ctx* c, const float* frames, int64_t n, int3
     return rc;
 }
 
+int spkdiar_features_upload_batch(spkdiar_ctx* c, const float* const* frames, const int64_t* n, int32_t nrec,
+                                  int32_t dim, spkdiar_feat** out, int64_t* base_out) {
+    if (!c || !out || !frames || !n || !base_out || nrec < 1)
+        return c ? set_err(c, SPKDIAR_E_ARG, "null argument / empty batch") : SPKDIAR_E_ARG;
+    if (nrec > 65535) return set_err(c, SPKDIAR_E_ARG, "at most 65535 recordings per batch");
+    std::vector<RecTab> tab((size_t)nrec);
+    int64_t rows = 0, max_tiles = 1;
+    for (int32_t r = 0; r < nrec; ++r) {
+        if (n[r] < 0 || (n[r] > 0 && !frames[r])) return set_err(c, SPKDIAR_E_ARG, "recording %d: bad frame count / null matrix", r);
+        const int64_t tiles = n[r] / K1_TILE + 1;          // the last block is partial or empty (stats.cuh)
+        tab[r].base = rows; tab[r].n = n[r];
+        base_out[r] = rows;
+        rows += tiles * K1_TILE;
+        max_tiles = std::max(max_tiles, tiles);
+    }
+    int rc = feat_alloc(c, rows, dim, out, nrec);
+    if (rc) return rc;
+    spkdiar_feat* f = *out;
+    f->nrec = nrec; f->max_tiles = max_tiles;
+    float* dx = nullptr;
+    cudaError_t e = pool_alloc(c, (size_t)rows * dim * sizeof(float), (void**)&dx);
+    if (e == cudaSuccess) { f->x = dx; f->own_x = true; e = pool_alloc(c, (size_t)nrec * sizeof(RecTab), &f->tab); }
+    if (e != cudaSuccess) {
+        spkdiar_features_free(f); *out = nullptr;
+        return set_err(c, SPKDIAR_E_NOMEM, "device allocation for the packed frames failed: %s", cudaGetErrorString(e));
+    }
+    {
+        Prof p(c, SPKDIAR_PROF_H2D);
+        e = cudaMemsetAsync(dx, 0, (size_t)rows * dim * sizeof(float), c->stream);      // the padding rows
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(f->tab, tab.data(), (size_t)nrec * sizeof(RecTab), cudaMemcpyHostToDevice, c->stream);
+        for (int32_t r = 0; r < nrec && e == cudaSuccess; ++r)
+            if (n[r] > 0)
+                e = cudaMemcpyAsync(dx + tab[r].base * dim, frames[r], (size_t)n[r] * dim * sizeof(float),
+                                    cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);       // `tab` is a host temporary
+    }
+    if (e != cudaSuccess) {
+        spkdiar_features_free(f); *out = nullptr;
+        return set_err(c, SPKDIAR_E_CUDA, "packed feature upload failed: %s", cudaGetErrorString(e));
+    }
+    rc = spkdiar_stats_build(f);
+    if (rc) { spkdiar_features_free(f); *out = nullptr; }
+    return rc;
+}
+
 int spkdiar_features_adopt(spkdiar_ctx* c, const float* dev_frames, int64_t n, int32_t dim, spkdiar_feat** out) {
     if (!c || !out || (!dev_frames && n > 0)) return c ? set_err(c, SPKDIAR_E_ARG, "null argument") : SPKDIAR_E_ARG;
     int rc = feat_alloc(c, n, dim, out);
@@ -230,6 +287,7 @@ int spkdiar_features_free(spkdiar_feat* f) {
     pool_free(f->ctx, f->shift);
     pool_free(f->ctx, f->chunk);
     pool_free(f->ctx, f->tile);
+    pool_free(f->ctx, f->tab);
     if (f->own_x) pool_free(f->ctx, f->x);
     delete f;
     return SPKDIAR_OK;
@@ -381,3 +439,4 @@ int spkdiar_score_sets(spkdiar_feat* f, int64_t npairs,
 
 #include "abi_gw.inc"
 #include "abi_cluster.inc"
+#include "abi_batch.inc"

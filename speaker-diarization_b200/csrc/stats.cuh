@@ -58,7 +58,7 @@ inline void fill_lut(uint8_t* row, uint8_t* col) {
 
 // per-file shift: mean of up to ~2048 evenly spaced frames (any constant works;
 // it only has to be near the mean and identical for every record of the file)
-__global__ void __launch_bounds__(1024) k1_shift(const float* __restrict__ x, int64_t n, double* __restrict__ shift) {
+__device__ __forceinline__ void k1_shift_body(const float* __restrict__ x, int64_t n, double* __restrict__ shift) {
     __shared__ double part[25][K1_XS];
     const int g = threadIdx.x / K1_XS, j = threadIdx.x % K1_XS;
     const int64_t step = n > 2048 ? n / 2048 : 1;
@@ -73,6 +73,24 @@ __global__ void __launch_bounds__(1024) k1_shift(const float* __restrict__ x, in
         for (int k = 0; k < 25; ++k) t += part[k][threadIdx.x];
         shift[threadIdx.x] = (threadIdx.x < D39 && ns > 0) ? t / (double)ns : 0.0;
     }
+}
+__global__ void __launch_bounds__(1024) k1_shift(const float* __restrict__ x, int64_t n, double* __restrict__ shift) {
+    k1_shift_body(x, n, shift);
+}
+
+// ---- packed batches of recordings (spkdiar_features_upload_batch) -------------------------
+// Recording r occupies the packed frame rows [base, base + n); base is a multiple of K1_TILE
+// and the recording owns n / K1_TILE + 1 blocks (its last block is partial or empty), so that
+// the record at its end - P[base + n], C[block of base + n] - never coincides with the zero
+// record that starts the next recording.  Shift, block-local prefix and block-level scan all
+// restart per recording: the statistics of a packed recording are bit-identical to those of
+// the same recording uploaded alone.
+struct RecTab { int64_t base; int64_t n; };
+
+__global__ void __launch_bounds__(1024) k1_shift_batch(const float* __restrict__ x, const RecTab* __restrict__ tab,
+                                                       double* __restrict__ shift) {
+    const RecTab t = tab[blockIdx.x];
+    k1_shift_body(x + t.base * D39, t.n, shift + (int64_t)blockIdx.x * K1_XS);
 }
 
 __device__ __forceinline__ void k1_load_tile(const float* __restrict__ x, int64_t n, int64_t f0,
@@ -130,8 +148,8 @@ __device__ __forceinline__ void dd_add(double& hi, double& lo, double v) {      
     hi = h2;
 }
 
-__global__ void __launch_bounds__(128) k1_chunk_sums(const double* __restrict__ tile, int64_t ntiles,
-                                                     double2* __restrict__ chunk_tot) {
+__device__ __forceinline__ void k1_chunk_sums_body(const double* __restrict__ tile, int64_t ntiles,
+                                                   double2* __restrict__ chunk_tot) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= K1_CHUNKS * REC) return;
     const int ch = idx / REC, q = idx - ch * REC;
@@ -149,10 +167,14 @@ __global__ void __launch_bounds__(128) k1_chunk_sums(const double* __restrict__ 
     for (; t < t1; ++t) dd_add(hi, lo, tile[t * REC + q]);
     chunk_tot[idx] = make_double2(hi, lo);
 }
+__global__ void __launch_bounds__(128) k1_chunk_sums(const double* __restrict__ tile, int64_t ntiles,
+                                                     double2* __restrict__ chunk_tot) {
+    k1_chunk_sums_body(tile, ntiles, chunk_tot);
+}
 
-__global__ void __launch_bounds__(128) k1_chunk_scan(const double* __restrict__ tile, int64_t ntiles,
-                                                     const double2* __restrict__ chunk_tot,
-                                                     double2* __restrict__ C) {
+__device__ __forceinline__ void k1_chunk_scan_body(const double* __restrict__ tile, int64_t ntiles,
+                                                   const double2* __restrict__ chunk_tot,
+                                                   double2* __restrict__ C, bool write_total) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= K1_CHUNKS * REC) return;
     const int ch = idx / REC, q = idx - ch * REC;
@@ -174,15 +196,44 @@ __global__ void __launch_bounds__(128) k1_chunk_scan(const double* __restrict__ 
     }
     for (; t < t1; ++t) { C[t * REC + q] = make_double2(hi, lo); dd_add(hi, lo, tile[t * REC + q]); }
     // the thread that owns the last block also writes the grand total
-    if (t1 == ntiles && t0 < ntiles) C[ntiles * REC + q] = make_double2(hi, lo);
+    if (write_total && t1 == ntiles && t0 < ntiles) C[ntiles * REC + q] = make_double2(hi, lo);
+}
+__global__ void __launch_bounds__(128) k1_chunk_scan(const double* __restrict__ tile, int64_t ntiles,
+                                                     const double2* __restrict__ chunk_tot,
+                                                     double2* __restrict__ C) {
+    k1_chunk_scan_body(tile, ntiles, chunk_tot, C, true);
+}
+// packed batch: blockIdx.y = recording.  The scan runs over ceil(n / K1_TILE) blocks exactly as for
+// a recording uploaded alone; the total lands in the recording's own extra block when n is a
+// multiple of K1_TILE and is not written otherwise (the slot would be the next recording's zero).
+__global__ void __launch_bounds__(128) k1_chunk_sums_batch(const double* __restrict__ tile, const RecTab* __restrict__ tab,
+                                                           double2* __restrict__ chunk_tot) {
+    const RecTab t = tab[blockIdx.y];
+    const int64_t nt = (t.n + K1_TILE - 1) / K1_TILE;
+    if (nt == 0) return;
+    k1_chunk_sums_body(tile + (t.base / K1_TILE) * REC, nt, chunk_tot + (int64_t)blockIdx.y * K1_CHUNKS * REC);
+}
+__global__ void __launch_bounds__(128) k1_chunk_scan_batch(const double* __restrict__ tile, const RecTab* __restrict__ tab,
+                                                           const double2* __restrict__ chunk_tot,
+                                                           double2* __restrict__ C) {
+    const RecTab t = tab[blockIdx.y];
+    const int64_t nt = (t.n + K1_TILE - 1) / K1_TILE;
+    const int64_t t0 = t.base / K1_TILE;
+    if (nt == 0) {                                   // an empty recording: its one block prefix is zero
+        const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+        if (idx < REC) C[t0 * REC + idx] = make_double2(0.0, 0.0);
+        return;
+    }
+    k1_chunk_scan_body(tile + t0 * REC, nt, chunk_tot + (int64_t)blockIdx.y * K1_CHUNKS * REC, C + t0 * REC,
+                       t.n % K1_TILE == 0);
 }
 
 // one CTA per block of K1_TILE frames: P[f0] = 0, P[f0 + t + 1] = running sums
 // (t + 1 < K1_TILE), block total -> tile[]
-__global__ void __launch_bounds__(K1_THREADS) k1_tile_write(const float* __restrict__ x, int64_t n,
-                                                            const double* __restrict__ shift,
-                                                            double* __restrict__ tile,
-                                                            double* __restrict__ P) {
+__device__ __forceinline__ void k1_tile_write_body(const float* __restrict__ x, int64_t n,
+                                                   const double* __restrict__ shift,
+                                                   double* __restrict__ tile,
+                                                   double* __restrict__ P) {
     __shared__ __align__(16) double xs[K1_TILE][K1_XS];
     const int64_t f0 = (int64_t)blockIdx.x * K1_TILE;
     k1_load_tile(x, n, f0, shift, xs);
@@ -204,6 +255,23 @@ __global__ void __launch_bounds__(K1_THREADS) k1_tile_write(const float* __restr
     tile[(int64_t)blockIdx.x * REC + q] = acc;
     // a recording that ends exactly on a block boundary still needs its last (zero) record
     if (valid == K1_TILE && f0 + K1_TILE == n) __stcs(out + (int64_t)K1_TILE * REC, 0.0);
+}
+__global__ void __launch_bounds__(K1_THREADS) k1_tile_write(const float* __restrict__ x, int64_t n,
+                                                            const double* __restrict__ shift,
+                                                            double* __restrict__ tile,
+                                                            double* __restrict__ P) {
+    k1_tile_write_body(x, n, shift, tile, P);
+}
+// packed batch: blockIdx.y = recording, blockIdx.x = block of the recording (n / K1_TILE + 1 of them)
+__global__ void __launch_bounds__(K1_THREADS) k1_tile_write_batch(const float* __restrict__ x,
+                                                                  const RecTab* __restrict__ tab,
+                                                                  const double* __restrict__ shift,
+                                                                  double* __restrict__ tile,
+                                                                  double* __restrict__ P) {
+    const RecTab t = tab[blockIdx.y];
+    if ((int64_t)blockIdx.x > t.n / K1_TILE) return;
+    k1_tile_write_body(x + t.base * D39, t.n, shift + (int64_t)blockIdx.y * K1_XS,
+                       tile + (t.base / K1_TILE) * REC, P + t.base * REC);
 }
 
 }  // namespace spk
