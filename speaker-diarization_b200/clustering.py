@@ -49,6 +49,7 @@ class Clusterer(object):
         self.feapath = feapath
         self.feaext = feaext
         self.log = log if log is not None else (lambda *a: None)
+        self.quiet = log is None       # nobody reads the log: skip formatting it (corpus driver)
         self.writer = Writer(self.rate, rename=not dlr, segprefix=segpath or None)
         self.max_dist = 0
         self.min_dist = MAXINT
@@ -226,7 +227,8 @@ class Clusterer(object):
         use_device = self.engine == 'device' and self.metric != _abi.KL2
         merges = self._merge_sequence_device(feat) if use_device else self._merge_sequence_host(feat)
         for a, b, d in merges:
-            self.log(p2line('Merging:', a + 1, 'and', b + 1, 'distance:', d))
+            if not self.quiet:
+                self.log(p2line('Merging:', a + 1, 'and', b + 1, 'distance:', d))
             speakers[a].extend(speakers[b])
             speakers.pop(b)
         self.merges = merges

@@ -98,6 +98,19 @@ struct GwDev {                 // kernel parameters
     int64_t win_cap;
     unsigned long long* nwin;  // output slots claimed (blocks of GW_SLOT_BLOCK; unused slots keep chain = -1)
     unsigned long long* nrec;  // records produced
+    // split mode (abi_gw.inc: one long chain cut into sub-chains that run side by side, one CTA each):
+    // a sub-chain publishes the absolute position of every change it detects and stops as soon as one
+    // of them is also a change of a LATER sub-chain - from an identical `start` on, two searches are
+    // identical (CD:263-268: after a change the whole state is a function of `start`) -, or when it
+    // passes its give-up limits.  chg == nullptr: plain mode.
+    const double* start0;      // [nchain] initial chain-relative start (0 or a half frame)
+    const double* stop;        // [nchain][2] give up after a change at start >= stop[0] / a window end >= stop[1]
+    const int32_t* sync;       // [nchain][3] own slot, first and last + 1 slot to compare with
+    const double* slot_pos0;   // [nslot] absolute start position of the slot's sub-chain (increasing within a range)
+    double* chg;               // [nslot][chg_cap] published absolute change positions
+    int32_t* nchg;             // [nslot]
+    int32_t chg_cap;
+    int32_t* reason;           // [nchain] 0: the search ended as the reference's does, 1: synced, 2: gave up
     long long* trace;          // optional per-wave trace of CTA 0 (KL2)
     unsigned long long* dbg;   // optional phase cycle counters of CTA 0: plan, eval, barrier, decide, waves, tasks
 };
@@ -588,7 +601,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
         const int64_t nfr = g.seg_b[chain] - base;
         const double n = (double)nfr;
         GwState st;
-        st.start = 0.0;
+        st.start = g.chg ? __ldg(g.start0 + chain) : 0.0;
+        int reason = 0, nchg_mine = 0;              // split mode (warp 0, identical in all lanes)
         st.end = st.start + g.winsize * 2;
         st.ws = g.minfeas; st.dws = g.deltaws;
         st.left_valid = 0; st.seq = 0; st.coarse_waves = 0;
@@ -863,6 +877,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                         if (lane == fpos) { plan.pend_bk = bk; plan.pend_pl = plw; }
                     }
                     if (fin) st.done = true;
+                    if (g.chg && !st.done && !has_pos && st.end >= __ldg(g.stop + 2 * chain + 1)) { st.done = true; reason = 2; }
                     // every offset of the batch now has its left term / left side, and (KL2) a
                     // running right sum that ends at the last window of the batch
                     st.left_valid = plan.kmaxw;
@@ -899,6 +914,36 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     } else {
                         st.done = true;                                 // CD:269-270
                     }
+                    if (g.chg && !st.done) {
+                        const double apos = (double)base + st.start;
+                        const int slot = __ldg(g.sync + 3 * chain), lo = __ldg(g.sync + 3 * chain + 1), hi = __ldg(g.sync + 3 * chain + 2);
+                        double* mine = g.chg + (size_t)slot * g.chg_cap;
+                        if (nchg_mine < g.chg_cap && lane == 0) {
+                            mine[nchg_mine] = apos;
+                            __threadfence();
+                            *((volatile int32_t*)(g.nchg + slot)) = nchg_mine + 1;
+                        }
+                        ++nchg_mine;
+                        __syncwarp();
+                        const int nmine = nchg_mine < g.chg_cap ? nchg_mine : g.chg_cap;
+                        bool hit = false;
+                        for (int sl = lo; sl < hi && !hit; ++sl) {
+                            const double p0 = __ldg(g.slot_pos0 + sl);
+                            if (!(p0 <= apos)) break;                    // later sub-chains start beyond this change
+                            int nn = *((volatile int32_t*)(g.nchg + sl));
+                            nn = nn < g.chg_cap ? nn : g.chg_cap;
+                            __threadfence();
+                            int m0 = 0;                                  // my changes at or beyond that sub-chain's start
+                            while (m0 < nmine && __ldcg(mine + m0) < p0) ++m0;
+                            for (int i = lane; i < nn; i += 32) {
+                                const double v = __ldcg(g.chg + (size_t)sl * g.chg_cap + i);
+                                for (int m = m0; m < nmine; ++m) hit |= __ldcg(mine + m) == v;
+                            }
+                            hit = __any_sync(0xffffffffu, hit);
+                        }
+                        if (hit) { st.done = true; reason = 1; }
+                        else if (st.start >= __ldg(g.stop + 2 * chain)) { st.done = true; reason = 2; }
+                    }
                 }
                 __syncwarp();                                           // reads of the old plan before it is rewritten
                 plan_wave(st, n);
@@ -906,7 +951,10 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
             __syncthreads();
             t_eval += c2 - c1; t_bar += c3 - c2; t_dec += c4 - c3; t_plan += clock64() - c4; ++n_wave; n_task += plan.ntask;
         }
-        if (rank == 0 && threadIdx.x == 0) atomicAdd(g.nrec, (unsigned long long)st.seq);
+        if (rank == 0 && threadIdx.x == 0) {
+            atomicAdd(g.nrec, (unsigned long long)st.seq);
+            if (g.chg) g.reason[chain] = reason;
+        }
 
         // ---- next chain for this group ----
         if (g.ngroups >= g.nchain) break;           // every chain had its own group
