@@ -461,7 +461,7 @@ struct GwState {
     int pend_ncand, pend_ninf;
 };
 
-template <bool KL2>
+template <bool KL2, bool SPLIT>
 __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
     extern __shared__ __align__(16) unsigned char gw_smem[];
     GwPlan& plan = *reinterpret_cast<GwPlan*>(gw_smem);
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
         const int64_t nfr = g.seg_b[chain] - base;
         const double n = (double)nfr;
         GwState st;
-        st.start = g.chg ? __ldg(g.start0 + chain) : 0.0;
+        st.start = SPLIT ? __ldg(g.start0 + chain) : 0.0;
         int reason = 0, nchg_mine = 0;              // split mode (warp 0, identical in all lanes)
         st.end = st.start + g.winsize * 2;
         st.ws = g.minfeas; st.dws = g.deltaws;
@@ -877,7 +877,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                         if (lane == fpos) { plan.pend_bk = bk; plan.pend_pl = plw; }
                     }
                     if (fin) st.done = true;
-                    if (g.chg && !st.done && !has_pos && st.end >= __ldg(g.stop + 2 * chain + 1)) { st.done = true; reason = 2; }
+                    if (SPLIT && !st.done && !has_pos && st.end >= __ldg(g.stop + 2 * chain + 1)) { st.done = true; reason = 2; }
                     // every offset of the batch now has its left term / left side, and (KL2) a
                     // running right sum that ends at the last window of the batch
                     st.left_valid = plan.kmaxw;
@@ -914,7 +914,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     } else {
                         st.done = true;                                 // CD:269-270
                     }
-                    if (g.chg && !st.done) {
+                    if (SPLIT && !st.done) {
                         const double apos = (double)base + st.start;
                         const int slot = __ldg(g.sync + 3 * chain), lo = __ldg(g.sync + 3 * chain + 1), hi = __ldg(g.sync + 3 * chain + 2);
                         double* mine = g.chg + (size_t)slot * g.chg_cap;
@@ -953,7 +953,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
         }
         if (rank == 0 && threadIdx.x == 0) {
             atomicAdd(g.nrec, (unsigned long long)st.seq);
-            if (g.chg) g.reason[chain] = reason;
+            if (SPLIT) g.reason[chain] = reason;
         }
 
         // ---- next chain for this group ----
@@ -981,10 +981,14 @@ inline size_t gw_smem_bytes(bool kl2) {
 }
 
 inline cudaError_t gw_configure() {
-    cudaError_t e = cudaFuncSetAttribute(gw_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gw_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)gw_smem_bytes(false));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(gw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(gw_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gw_smem_bytes(false));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gw_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gw_smem_bytes(true));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gw_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)gw_smem_bytes(true));
 }
 
