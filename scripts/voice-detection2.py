@@ -1,0 +1,10 @@
+#!/usr/bin/env python3
+"""Drop-in for the reference's ./voice-detection2.py (same flags, same files in and out, same stdout
+text); host-only text glue around the hot path (speaker-diarization_b200/glue.py)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import spkdiar  # noqa: E402,F401
+from spkdiar import glue
+glue.vad_main()

@@ -76,7 +76,62 @@ def scoring_fixtures():
         print(name, len(stdout.splitlines()), 'report lines')
 
 
+def synthetic_exp(seed, nruns):
+    """A speech-activity token stream: alternating speech / silence runs (some shorter than the
+    hysteresis thresholds), repeated tokens inside long runs, ending in speech or silence."""
+    rng = numpy.random.default_rng(seed)
+    frame, toks = 0, []
+    speech = False
+    for _ in range(nruns):
+        n = int(rng.choice([8, 20, 30, 45, 120, 400, 900]))
+        tok = 'p' if speech else '<w>'
+        toks.append('%d %s' % (frame, tok))
+        if n >= 400:                                   # the decoder repeats the token inside long runs
+            toks.append('%d %s' % (frame + n // 2, tok))
+        frame += n
+        speech = not speech
+    return ' '.join(toks) + '\n', frame + int(rng.integers(1, 200))
+
+
+def glue_fixtures():
+    """voice-detection2.py and aku2ann.py of the reference on synthetic inputs."""
+    with tempfile.TemporaryDirectory() as tmp:
+        wavs = ['/syn/v%d.wav' % k for k in range(3)]
+        exps = {}
+        for k, w in enumerate(wavs):
+            text, last = synthetic_exp(3000 + k, 40 + 7 * k + (k % 2))
+            exps['v%d' % k] = dict(exp=text, last_frame='%d\n' % last)
+            open(os.path.join(tmp, 'v%d.exp' % k), 'w').write(text)
+            open(os.path.join(tmp, 'v%d.last_frame' % k), 'w').write('%d\n' % last)
+        recipe = ''.join('audio=%s\n' % w for w in wavs[:2]) + 'no audio here\n' + 'audio=%s\n' % wavs[2]
+        rp, outp = os.path.join(tmp, 'in.recipe'), os.path.join(tmp, 'out.recipe')
+        open(rp, 'w').write(recipe)
+        flags = ['-r', '125', '-ms', '0.2', '-mns', '0.3', '-sbe', '0.1', '-see', '0.05']
+        stdout, _ = ref_exec.run('voice-detection2.py', [rp, tmp, '-o', outp] + flags)
+        fix = dict(name='vad_recipe', script='voice-detection2.py', flags=flags, recipe_in=recipe, exps=exps,
+                   stdout=stdout.replace(tmp, '<TMP>'), recipe=open(outp).read())
+    json.dump(fix, open(os.path.join(HERE, 'vad_recipe.json'), 'w'), indent=1, sort_keys=True)
+    print('vad_recipe', fix['recipe'].count('\n'), 'turns')
+    with tempfile.TemporaryDirectory() as tmp:
+        src = json.load(open(os.path.join(HERE, 'cl1_hi_glr_ms.json')))['recipe']
+        lines = src.splitlines(True)
+        lines.insert(2, 'a line without fields\n')
+        lines.insert(4, 'audio=/syn/other.wav lna=b_1 start-time=1.5 end-time=2.25\n')
+        text = ''.join(lines)
+        rp, outp = os.path.join(tmp, 'in.recipe'), os.path.join(tmp, 'out.ann')
+        open(rp, 'w').write(text)
+        stdout, _ = ref_exec.run('aku2ann.py', [rp, '-o', outp])
+        fix = dict(name='aku2ann', script='aku2ann.py', recipe_in=text, stdout=stdout.replace(tmp, '<TMP>'),
+                   ann=open(outp).read())
+    json.dump(fix, open(os.path.join(HERE, 'aku2ann.json'), 'w'), indent=1, sort_keys=True)
+    print('aku2ann', fix['ann'].count('\n'), 'lines')
+
+
 if __name__ == '__main__':
-    if len(sys.argv) < 2 or sys.argv[1] != 'scoring':
-        main()
-    scoring_fixtures()
+    if len(sys.argv) > 1 and sys.argv[1] == 'glue':
+        glue_fixtures()
+    else:
+        if len(sys.argv) < 2 or sys.argv[1] != 'scoring':
+            main()
+        scoring_fixtures()
+        glue_fixtures()
