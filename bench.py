@@ -286,7 +286,7 @@ def run_other_workload(args):
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     ctx = _abi.Context(local, stream=torch.cuda.current_stream().cuda_stream)
-    W = max(args.warmup, 3)
+    W = max(args.warmup, 1 if args.workload == 'config5' else 3)     # a full-size config5 step takes seconds
 
     def barrier():
         if dist is not None:
@@ -326,17 +326,22 @@ def run_other_workload(args):
         hours_per_step, scaling = world * args.files * (60000 / RATE / 3600.0), 'weak'
         desc = ('config4: %d ten-minute recordings per GPU, spk-diarization2 flags (gw BIC change detection + CL1), '
                 'host frames through the drop-in API, %s' % (args.files, 'device batches of %d recordings (packed '
-                'statistics, one growing-window launch with one CTA per recording, one clustering launch)' % args.batch
+                'statistics, one growing-window launch with one CTA per recording, one clustering launch)%s' % (args.batch, ', device stages of the next batch overlapped with the host replay' if args.overlap else '')
                 if args.batch > 0 else 'one recording at a time'))
         pinned = [torch.from_numpy(frames).pin_memory() for _, _, frames in items]
 
         def step():
             out = None
             if args.batch > 0:
-                for b0 in range(0, len(items), args.batch):
-                    part = [(items[k][1], (pinned[k].data_ptr(), pinned[k].shape[0]))
-                            for k in range(b0, min(b0 + args.batch, len(items)))]
-                    out = corpus.diarize_batch(ctx, part, RATE)[-1]
+                parts = [[(items[k][1], (pinned[k].data_ptr(), pinned[k].shape[0]))
+                          for k in range(b0, min(b0 + args.batch, len(items)))]
+                         for b0 in range(0, len(items), args.batch)]
+                if args.overlap:
+                    for got in corpus.diarize_batches(ctx, parts, RATE):
+                        out = got[-1]
+                else:
+                    for part in parts:
+                        out = corpus.diarize_batch(ctx, part, RATE)[-1]
                 return out
             for name, lines, frames in items:
                 f = ctx.upload(frames)
@@ -385,6 +390,7 @@ def main():
     ap.add_argument('--segments', type=int, default=8000, help='config5: segments of the long recording')
     ap.add_argument('--files', type=int, default=16, help='config4: recordings per GPU')
     ap.add_argument('--batch', type=int, default=0, help='config4: recordings per device batch (0: one at a time)')
+    ap.add_argument('--overlap', action='store_true', help='config4 with --batch: overlap device stages and host replay')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

@@ -9,6 +9,7 @@ every entry point raises.
 import ctypes as C
 import os
 import os.path as op
+import threading
 
 import numpy as np
 
@@ -142,13 +143,34 @@ def nccl_unique_id():
     return buf.raw
 
 
+class _Serialised(object):
+    """``include/spkdiar.h``: "calls on one context are serialised by the caller".  This proxy
+    is that caller: every entry point reached through ``ctx.lib`` takes the context's lock, so a
+    worker thread may queue device work (ctypes releases the GIL inside the call) while another
+    thread replays records on the host (``corpus.run_corpus(..., overlap=True)``)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._lock = threading.RLock()
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        lock = self._lock
+
+        def call(*args):
+            with lock:
+                return fn(*args)
+        setattr(self, name, call)
+        return call
+
+
 class Context(object):
     """One device context (``spkdiar_ctx``).  ``stream``: an existing
     ``cudaStream_t`` as an int (e.g. ``torch.cuda.current_stream().cuda_stream``)
     or None."""
 
     def __init__(self, device=0, stream=None):
-        self.lib = load_library()
+        self.lib = _Serialised(load_library())
         h = C.c_void_p()
         rc = self.lib.spkdiar_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
         if rc != 0:

@@ -51,33 +51,38 @@ def diarize_recording(ctx, recipe_lines, frames_loader, frame_rate=125, threshol
     return seg.getvalue(), out.getvalue(), summary
 
 
-def diarize_batch(ctx, batch, frame_rate=125, threshold=0.0):
-    """A batch of recordings through change detection + clustering with the device work of the
-    WHOLE batch in four launches: packed upload + statistics, one growing-window launch over the
-    chains of all recordings (one CTA per chain), one clustering launch (one CTA per recording).
-    ``batch``: list of (recipe_lines, frames).  Returns [(segmentation recipe text, clustered
-    recipe text, summary)] - byte-identical to ``diarize_recording`` on each item (the packed
-    statistics restart per recording; the host replay is the same code)."""
-    from . import change_detection as pcd, clustering as pcl
-    pack = ctx.upload_batch([frames() if callable(frames) else frames for _, frames in batch])
-    try:
-        views = [pack.view(r) for r in range(len(batch))]
-        parsed = [recipe_mod.parse(lines) for lines, _ in batch]
-        dets = [pcd.Detector(frame_rate, threshold=threshold, ctx=ctx, **D2_CHANGE) for _ in batch]
-        # ---- change detection: every chain of every recording in one launch ----
-        groups = [det.gw_chains(rec, lambda l, v=v: v) for det, rec, v in zip(dets, parsed, views)]
-        flat = [(r, k) for r, grp in enumerate(groups) for k in range(len(grp))]
-        chains = [[] for _ in batch]
-        for r, k in flat:
-            chains[r].extend(groups[r][k][1])
-        d0 = dets[0]
-        results = pack.gw_run_batch(chains, d0.rate, d0.winsize, d0.winstep, d0.deltaws, d0.threshold,
-                                    d0.lambdac, d0.metric)
-        seg_lines = []
-        for r, (det, rec, v) in enumerate(zip(dets, parsed, views)):
-            win, first = results[r]
+class _BatchJob(object):
+    """One device batch on its way through the four stages of ``diarize_batch``:
+    A (device) packed upload + statistics + ONE growing-window launch over every chain,
+    B (host)   replay of the window records into segmentation recipes,
+    C (device) ONE clustering launch, one CTA per recording,
+    D (host)   replay of the merge sequences into clustered recipes."""
+
+    def __init__(self, ctx, batch, frame_rate, threshold):
+        from . import change_detection as pcd
+        self.ctx, self.batch, self.rate, self.threshold = ctx, batch, frame_rate, threshold
+        self.parsed = [recipe_mod.parse(lines) for lines, _ in batch]
+        self.dets = [pcd.Detector(frame_rate, threshold=threshold, ctx=ctx, **D2_CHANGE) for _ in batch]
+        self.pack = None
+
+    def stage_a(self):
+        self.pack = self.ctx.upload_batch([frames() if callable(frames) else frames for _, frames in self.batch])
+        self.views = [self.pack.view(r) for r in range(len(self.batch))]
+        self.groups = [det.gw_chains(rec, lambda l, v=v: v)
+                       for det, rec, v in zip(self.dets, self.parsed, self.views)]
+        chains = [[c for _, ch in grp for c in ch] for grp in self.groups]
+        d0 = self.dets[0]
+        self.gw = self.pack.gw_run_batch(chains, d0.rate, d0.winsize, d0.winstep, d0.deltaws, d0.threshold,
+                                         d0.lambdac, d0.metric)
+        return self
+
+    def stage_b(self):
+        from . import clustering as pcl
+        self.seg_lines = []
+        for r, (det, rec, v) in enumerate(zip(self.dets, self.parsed, self.views)):
+            win, first = self.gw[r]
             c0 = 0
-            for feat, ch in groups[r]:                       # usually one group: one wav per recipe
+            for feat, ch in self.groups[r]:                  # usually one group: one wav per recipe
                 lo, hi = int(first[c0]), int(first[c0 + len(ch)])
                 sub = win[lo:hi].copy()
                 sub['chain'] -= c0
@@ -85,30 +90,96 @@ def diarize_batch(ctx, batch, frame_rate=125, threshold=0.0):
                 c0 += len(ch)
             seg = io.StringIO()
             det.detect_changes(rec, seg, loader=lambda l, v=v: v)
-            seg_lines.append(seg.getvalue().splitlines(True))
-        # ---- clustering: one problem per recording, one launch ----
-        cls = [pcl.Clusterer(frame_rate, variant=1, threshold=threshold, ctx=ctx, **D2_CLUSTER) for _ in batch]
-        seg_parsed = [recipe_mod.parse(lines) for lines in seg_lines]
-        problems = [cl.initial_segments(rec, v.n) for cl, rec, v in zip(cls, seg_parsed, views)]
-        live = [r for r, p in enumerate(problems) if p]
-        merged = pack.cluster_batch([problems[r] for r in live], cls[0].metric, cls[0].lambdac,
-                                    threshold, 0, 1) if live else []
+            self.seg_lines.append(seg.getvalue().splitlines(True))
+        self.cls = [pcl.Clusterer(self.rate, variant=1, threshold=self.threshold, ctx=self.ctx, **D2_CLUSTER)
+                    for _ in self.batch]
+        self.seg_parsed = [recipe_mod.parse(lines) for lines in self.seg_lines]
+        self.problems = [cl.initial_segments(rec, v.n)
+                         for cl, rec, v in zip(self.cls, self.seg_parsed, self.views)]
+        self.live = [r for r, p in enumerate(self.problems) if p]
+        return self
+
+    def stage_c(self):
+        c0 = self.cls[0]
+        self.merged = self.pack.cluster_batch([self.problems[r] for r in self.live], c0.metric, c0.lambdac,
+                                              self.threshold, 0, 1) if self.live else []
+        return self
+
+    def stage_d(self):
         out = []
-        for r, (cl, rec, v) in enumerate(zip(cls, seg_parsed, views)):
-            if r in live:
-                cl.prefetch(v, problems[r], merged[live.index(r)])
+        where = {r: k for k, r in enumerate(self.live)}
+        for r, (cl, rec, v) in enumerate(zip(self.cls, self.seg_parsed, self.views)):
+            if r in where:
+                cl.prefetch(v, self.problems[r], self.merged[where[r]])
             clu = io.StringIO()
             cl.process_recipe(rec, clu, loader=lambda l, v=v: v)
-            summary = dict(turns=len(seg_lines[r]), speakers=len(cl.speakers), windows=dets[r].windows_visited,
-                           merges=len(cl.merges))
-            out.append((''.join(seg_lines[r]), clu.getvalue(), summary))
+            summary = dict(turns=len(self.seg_lines[r]), speakers=len(cl.speakers),
+                           windows=self.dets[r].windows_visited, merges=len(cl.merges))
+            out.append((''.join(self.seg_lines[r]), clu.getvalue(), summary))
         return out
+
+    def close(self):
+        if self.pack is not None:
+            self.pack.close()
+            self.pack = None
+
+
+def diarize_batch(ctx, batch, frame_rate=125, threshold=0.0):
+    """A batch of recordings through change detection + clustering with the device work of the
+    WHOLE batch in a handful of launches: packed upload + statistics, one growing-window launch over
+    the chains of all recordings (one CTA per chain), one clustering launch (one CTA per recording).
+    ``batch``: list of (recipe_lines, frames).  Returns [(segmentation recipe text, clustered
+    recipe text, summary)] - byte-identical to ``diarize_recording`` on each item (the packed
+    statistics restart per recording; the host replay is the same code)."""
+    job = _BatchJob(ctx, batch, frame_rate, threshold)
+    try:
+        return job.stage_a().stage_b().stage_c().stage_d()
     finally:
-        pack.close()
+        job.close()
+
+
+def diarize_batches(ctx, batches, frame_rate=125, threshold=0.0):
+    """``diarize_batch`` over a sequence of batches with the stages OVERLAPPED: a worker thread
+    queues the device stages (the context's calls are serialised; ctypes releases the GIL inside
+    them) while this thread replays records.  While the host replays batch k, the device already
+    uploads batch k + 1 and searches it; the clustering launch of batch k queues behind.  Up to
+    three packed batches are resident at a time (6,560 B per frame each).  Yields the result list
+    of every batch, in order; results are those of ``diarize_batch``."""
+    from concurrent.futures import ThreadPoolExecutor
+    batches = list(batches)
+    if not batches:
+        return
+    with ThreadPoolExecutor(max_workers=1) as dev:
+        jobs = [_BatchJob(ctx, b, frame_rate, threshold) for b in batches]
+        try:
+            fa = dev.submit(jobs[0].stage_a)
+            prev = None                                         # (job, future of its stage C)
+            for k, job in enumerate(jobs):
+                fa.result()
+                if k + 1 < len(jobs):
+                    fa = dev.submit(jobs[k + 1].stage_a)        # device: upload + search of the next batch ...
+                job.stage_b()                                   # ... while the host replays this one
+                fc = dev.submit(job.stage_c)
+                if prev is not None:
+                    prev[1].result()
+                    out = prev[0].stage_d()
+                    dev.submit(prev[0].close)
+                    yield out
+                prev = (job, fc)
+            prev[1].result()
+            out = prev[0].stage_d()
+            dev.submit(prev[0].close).result()
+            yield out
+        finally:
+            for job in jobs:
+                try:
+                    dev.submit(job.close).result()
+                except Exception:           # pragma: no cover - the first error is the one to report
+                    pass
 
 
 def run_corpus(items, rank=0, world=1, device=None, outdir=None, frame_rate=125, runner=None,
-               gather=None, batch=0):
+               gather=None, batch=0, overlap=False):
     """Diarize the items this rank owns.
 
     ``items``  list of (name, recipe_lines, frames) with ``frames`` a float32
@@ -119,6 +190,8 @@ def run_corpus(items, rank=0, world=1, device=None, outdir=None, frame_rate=125,
                ``torch.distributed.all_gather_object``); None = single process.
     ``batch``  recordings per device batch (``diarize_batch``: the device work of the whole
                batch in four launches); 0 = one recording at a time.
+    ``overlap`` with ``batch``: device stages of the next batch run while the host replays the
+               current one (``diarize_batches``).
 
     Returns {name: summary} for the WHOLE corpus on every rank (after the
     gather) - results do not depend on the number of ranks.
@@ -140,9 +213,11 @@ def run_corpus(items, rank=0, world=1, device=None, outdir=None, frame_rate=125,
                     feat.close()
         results = []
         if batch > 0 and ctx is not None:
-            for b0 in range(0, len(mine), batch):
-                part = [items[k] for k in mine[b0:b0 + batch]]
-                got = diarize_batch(ctx, [(lines, frames) for _, lines, frames in part], frame_rate)
+            parts = [[items[k] for k in mine[b0:b0 + batch]] for b0 in range(0, len(mine), batch)]
+            plain = [[(lines, frames) for _, lines, frames in part] for part in parts]
+            gen = diarize_batches(ctx, plain, frame_rate) if overlap else \
+                (diarize_batch(ctx, b, frame_rate) for b in plain)
+            for part, got in zip(parts, gen):
                 results.extend((name,) + g for (name, _, _), g in zip(part, got))
         else:
             for k in mine:

@@ -141,3 +141,20 @@ def test_diarize_batch_equals_one_at_a_time_and_oracle(ctx):
     out = io.StringIO()
     oc.process_recipe(recipe_mod.parse(seg.getvalue().splitlines(True)), out, loader=lambda l: (39, frames))
     assert out.getvalue() == batched[1][1]
+
+
+def test_overlapped_batches_equal_batches(ctx):
+    """The pipelined driver (device stages on a worker thread, host replay on this one) returns
+    exactly what the synchronous one returns, batch by batch."""
+    batches = []
+    for b in range(4):
+        part = []
+        for k in range(3 + b % 2):
+            rec = synth.make_recording(950 + 10 * b + k, 4000 + 500 * k, 2 + k % 3, turn_lo=3, turn_hi=9)
+            part.append((synth.one_line_recipe('/syn/o%d_%d.wav' % (b, k), rec), rec.frames))
+        batches.append(part)
+    want = [corpus.diarize_batch(ctx, part, 100) for part in batches]
+    got = list(corpus.diarize_batches(ctx, batches, 100))
+    assert got == want
+    assert list(corpus.diarize_batches(ctx, [], 100)) == []
+    assert list(corpus.diarize_batches(ctx, batches[:1], 100)) == want[:1]
