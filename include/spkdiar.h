@@ -194,6 +194,12 @@ int  spkdiar_gw_run_multi(spkdiar_feat* f, int32_t nrun, const spkdiar_gw_params
                           spkdiar_gw_window* const* win, const int64_t* win_cap,
                           int64_t* const* win_first);
 
+/* Host-only self-test of the sub-chain split / stitch / continuation logic behind spkdiar_gw_run (no
+ * device needed): a toy search whose state after a change depends on `start` alone is cut into
+ * sub-chains, stitched round by round by the real code and compared with the toy's sequential search.
+ * p_sync: probability that searches from different starts agree on a change.  0 = passed. */
+int  spkdiar_selftest_stitch(uint64_t seed, double p_sync, int64_t nframes, int32_t nsub_target);
+
 /* ---- agglomerative clustering (K5-K7) ---------------------------------------
  * Replaces spk_cluster_hi of spk-clustering.py:178-260 (variant 1) and of
  * spk-clustering2.py:173-229 (variant 2).  Initial clusters are the frame

@@ -34,7 +34,7 @@ SYMBOLS = (
     'spkdiar_cluster_run_sharded_p2p', 'spkdiar_mailbox_create', 'spkdiar_mailbox_open',
     'spkdiar_mailbox_close', 'spkdiar_mailbox_free',
     'spkdiar_cluster_free', 'spkdiar_cluster_matrix',
-    'spkdiar_features_upload_batch', 'spkdiar_cluster_batch',
+    'spkdiar_features_upload_batch', 'spkdiar_cluster_batch', 'spkdiar_selftest_stitch',
 )
 
 
@@ -121,6 +121,7 @@ def load_library(path=None):
         'spkdiar_cluster_matrix': (C.c_int, [vp, pdbl, C.POINTER(C.c_uint8)]),
         'spkdiar_features_upload_batch': (C.c_int, [vp, C.POINTER(vp), pi64, i32, i32, C.POINTER(vp), pi64]),
         'spkdiar_cluster_batch': (C.c_int, [vp, i32, pi64, pi64, pi64, C.c_int, dbl, dbl, i32, i32, vp, pi64, pdbl]),
+        'spkdiar_selftest_stitch': (C.c_int, [C.c_uint64, dbl, i64, i32]),
     }
     for name, (res, args) in proto.items():
         fn = getattr(lib, name)
