@@ -126,17 +126,27 @@ def device_step(ctx, dev_ptr, nframes):
         # the three searches are independent dependent chains: side by side on disjoint SM subsets
         runs = [dict(rate=float(RATE), winsize=W, winstep=ST, deltaws=DW, threshold=thr, lambdac=1.0, metric=met)
                 for met, thr in ((_abi.BIC, 0.0), (_abi.GLR, GLR_T), (_abi.KL2, KL2_T))]
+        def cluster_bic():
+            sa, sb = segments_from_windows(out['BIC'], nframes)
+            with feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
+                out['merges'] = cl.run(0.0, 0, 1)[0]
+            out['nseg'] = len(sa)
         if SEQUENTIAL:
-            res = [feat.gw_run([0], [nframes], **r) for r in runs]
+            for name, r in zip(('BIC', 'GLR', 'KL2'), runs):
+                out[name] = feat.gw_run([0], [nframes], **r)[0]
+            cluster_bic()
         else:
-            res = feat.gw_run_multi([0], [nframes], runs)
-        for name, (win, _) in zip(('BIC', 'GLR', 'KL2'), res):
-            out[name] = win
-        sa, sb = segments_from_windows(out['BIC'], nframes)
-        with feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
-            merges, _ = cl.run(0.0, 0, 1)
-        out['merges'] = merges
-        out['nseg'] = len(sa)
+            # all three searches are launched together; the BIC one (split into sub-chains, done first) is
+            # collected and its turns are clustered on the SMs it ran on while the KL2 chain is still running
+            with feat.gw_multi_begin([0], [nframes], runs) as h:
+                out['BIC'] = h.wait(0)[0]
+                ctx.exec_on(*h.where(0))
+                try:
+                    cluster_bic()
+                finally:
+                    ctx.exec_on()
+                out['GLR'] = h.wait(1)[0]
+                out['KL2'] = h.wait(2)[0]
     finally:
         feat.close()
     return out
@@ -183,17 +193,26 @@ def e2e_step(ctx, host_frames, recipe_lines):
         dets = [pcd.Detector(RATE, 'gw', name, GW_FLAGS['winsize'], GW_FLAGS['winstep'], GW_FLAGS['deltaws'],
                              thr, 1.0, ctx=ctx) for name, thr in zip(names, (0.0, GLR_T, KL2_T))]
         bufs = [io.StringIO() for _ in names]
+        def cluster_bic(det, where):
+            # spk-clustering.py on the recipe the BIC detector has just written - queued on the stream and
+            # SMs its search ran on, while the GLR and KL2 searches are still running
+            if where is not None:
+                ctx.exec_on(*where)
+            try:
+                cl = pcl.Clusterer(RATE, 1, 'hi', 'BIC', 0.0, 0, 1.3, ctx=ctx)
+                buf = io.StringIO()
+                cl.process_recipe(recipe.parse(bufs[0].getvalue().splitlines(True)), buf, loader=lambda l: feat)
+                texts['clusters'] = buf.getvalue()
+            finally:
+                ctx.exec_on()
         if SEQUENTIAL:
             for det, buf in zip(dets, bufs):
                 det.detect_changes(parsed, buf, loader=lambda l: feat)
+            cluster_bic(dets[0], None)
         else:
-            pcd.detect_changes_multi(dets, parsed, bufs, loader=lambda l: feat)
+            pcd.detect_changes_multi(dets, parsed, bufs, loader=lambda l: feat, after={0: cluster_bic})
         for name, buf in zip(names, bufs):
             texts[name] = buf.getvalue()
-        cl = pcl.Clusterer(RATE, 1, 'hi', 'BIC', 0.0, 0, 1.3, ctx=ctx)
-        buf = io.StringIO()
-        cl.process_recipe(recipe.parse(texts['BIC'].splitlines(True)), buf, loader=lambda l: feat)
-        texts['clusters'] = buf.getvalue()
     finally:
         feat.close()
     return texts

@@ -194,6 +194,24 @@ int  spkdiar_gw_run_multi(spkdiar_feat* f, int32_t nrun, const spkdiar_gw_params
                           spkdiar_gw_window* const* win, const int64_t* win_cap,
                           int64_t* const* win_first);
 
+/* The same searches as an asynchronous object.  begin() launches them (searches that run split into
+ * sub-chains share one stream and one set of SMs: the first starts at once, the others when they are
+ * waited for); wait(run) blocks until search `run` is complete and fills its records as spkdiar_gw_run
+ * does (SPKDIAR_E_CAPACITY: wait again with a larger buffer); where(run) tells on which stream and how
+ * many SMs that search ran, so that work depending on it (spkdiar_ctx_exec + the clustering of its
+ * turns) can be queued there while the other searches are still running; end() releases the object
+ * (and waits for searches nobody collected).  One such object per context at a time. */
+typedef struct spkdiar_gwm spkdiar_gwm;
+int  spkdiar_gw_multi_begin(spkdiar_feat* f, int32_t nrun, const spkdiar_gw_params* params,
+                            const int64_t* seg_a, const int64_t* seg_b, int32_t nchain, spkdiar_gwm** out);
+int  spkdiar_gw_multi_wait(spkdiar_gwm* h, int32_t run, spkdiar_gw_window* win, int64_t win_cap,
+                           int64_t* win_first);
+int  spkdiar_gw_multi_where(const spkdiar_gwm* h, int32_t run, void** stream, int32_t* sms);
+int  spkdiar_gw_multi_end(spkdiar_gwm* h);
+/* Later calls on ctx run on `stream` (a cudaStream_t) with at most `sms` SMs; (NULL, 0) restores the
+ * context's own stream and the whole device. */
+int  spkdiar_ctx_exec(spkdiar_ctx* ctx, void* stream, int32_t sms);
+
 /* Host-only self-test of the sub-chain split / stitch / continuation logic behind spkdiar_gw_run (no
  * device needed): a toy search whose state after a change depends on `start` alone is cut into
  * sub-chains, stitched round by round by the real code and compared with the toy's sequential search.

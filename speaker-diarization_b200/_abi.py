@@ -35,6 +35,8 @@ SYMBOLS = (
     'spkdiar_mailbox_close', 'spkdiar_mailbox_free',
     'spkdiar_cluster_free', 'spkdiar_cluster_matrix',
     'spkdiar_features_upload_batch', 'spkdiar_cluster_batch', 'spkdiar_selftest_stitch',
+    'spkdiar_gw_multi_begin', 'spkdiar_gw_multi_wait', 'spkdiar_gw_multi_where', 'spkdiar_gw_multi_end',
+    'spkdiar_ctx_exec',
 )
 
 
@@ -122,6 +124,11 @@ def load_library(path=None):
         'spkdiar_features_upload_batch': (C.c_int, [vp, C.POINTER(vp), pi64, i32, i32, C.POINTER(vp), pi64]),
         'spkdiar_cluster_batch': (C.c_int, [vp, i32, pi64, pi64, pi64, C.c_int, dbl, dbl, i32, i32, vp, pi64, pdbl]),
         'spkdiar_selftest_stitch': (C.c_int, [C.c_uint64, dbl, i64, i32]),
+        'spkdiar_gw_multi_begin': (C.c_int, [vp, i32, C.POINTER(GwParams), pi64, pi64, i32, C.POINTER(vp)]),
+        'spkdiar_gw_multi_wait': (C.c_int, [vp, i32, vp, i64, pi64]),
+        'spkdiar_gw_multi_where': (C.c_int, [vp, i32, C.POINTER(vp), C.POINTER(i32)]),
+        'spkdiar_gw_multi_end': (C.c_int, [vp]),
+        'spkdiar_ctx_exec': (C.c_int, [vp, vp, i32]),
     }
     for name, (res, args) in proto.items():
         fn = getattr(lib, name)
@@ -211,6 +218,11 @@ class Context(object):
         n = np.zeros(NPROF, dtype=np.int64)
         self._check(self.lib.spkdiar_profile_read(self.h, _p(ms, C.c_double), _p(n, C.c_int64)))
         return {PROF_NAMES[k]: (float(ms[k]), int(n[k])) for k in range(NPROF)}
+
+    def exec_on(self, stream=None, sms=0):
+        """Later calls run on ``stream`` (int) with at most ``sms`` SMs; no arguments restore the
+        context's own stream and the whole device (``spkdiar_ctx_exec``)."""
+        self._check(self.lib.spkdiar_ctx_exec(self.h, C.c_void_p(stream) if stream else None, int(sms)))
 
     def upload(self, frames):
         """(n, 39) float32 host matrix -> Features (copied to HBM, statistics built)."""
@@ -375,6 +387,10 @@ class Features(object):
             self.ctx._check(rc)
             return [(wins[k][:int(firsts[k][nchain])], firsts[k]) for k in range(nrun)]
 
+    def gw_multi_begin(self, seg_a, seg_b, runs, max_groups=0):
+        """Asynchronous form of ``gw_run_multi``: -> GwMulti (``wait(r)`` per search, ``close()``)."""
+        return GwMulti(self, seg_a, seg_b, runs, max_groups)
+
     def cluster(self, seg_a, seg_b, metric, lambdac=1.3):
         seg_a, seg_b = _i64(seg_a), _i64(seg_b)
         h = C.c_void_p()
@@ -382,6 +398,56 @@ class Features(object):
             self.h, _p(seg_a, C.c_int64), _p(seg_b, C.c_int64), seg_a.shape[0], int(metric),
             float(lambdac), C.byref(h)))
         return Clusters(self, h, seg_a.shape[0])
+
+
+class GwMulti(object):
+    """``spkdiar_gwm``: several growing-window searches over the same chains, launched together;
+    ``wait(r)`` collects search r while the others keep running, ``where(r)`` names the stream
+    and SM share it ran on (for ``Context.exec_on``: queue the clustering of its turns there)."""
+
+    def __init__(self, feat, seg_a, seg_b, runs, max_groups=0):
+        self.ctx = feat.ctx
+        self.seg_a, self.seg_b = _i64(seg_a), _i64(seg_b)
+        self.nchain = self.seg_a.shape[0]
+        self.runs = runs
+        prm = (GwParams * len(runs))(*[GwParams(float(r['rate']), float(r['winsize']), float(r['winstep']),
+                                                float(r['deltaws']), float(r['threshold']), float(r['lambdac']),
+                                                int(r['metric']), int(max_groups)) for r in runs])
+        h = C.c_void_p()
+        self.ctx._check(self.ctx.lib.spkdiar_gw_multi_begin(feat.h, len(runs), prm, _p(self.seg_a, C.c_int64),
+                                                            _p(self.seg_b, C.c_int64), self.nchain, C.byref(h)))
+        self.h = h
+
+    def wait(self, r):
+        """-> (window records, win_first) of search r, as ``Features.gw_run`` returns them."""
+        unit = max(float(self.runs[r]['rate']) / 2 - float(self.runs[r]['rate']) / 10, 1.0)
+        cap = int(sum(2 * ((b - a) / unit + 2) for a, b in zip(self.seg_a, self.seg_b))) + 16
+        first = np.zeros(self.nchain + 1, dtype=np.int64)
+        while True:
+            win = np.zeros(cap, dtype=GW_WINDOW_DTYPE)
+            rc = self.ctx.lib.spkdiar_gw_multi_wait(self.h, int(r), win.ctypes.data_as(C.c_void_p), cap,
+                                                    _p(first, C.c_int64))
+            if rc == -4 and first[0] > cap:
+                cap = int(first[0])
+                continue
+            self.ctx._check(rc)
+            return win[:int(first[self.nchain])], first
+
+    def where(self, r):
+        st, sms = C.c_void_p(), C.c_int32(0)
+        self.ctx._check(self.ctx.lib.spkdiar_gw_multi_where(self.h, int(r), C.byref(st), C.byref(sms)))
+        return st.value, int(sms.value)
+
+    def close(self):
+        if getattr(self, 'h', None) and self.ctx.h:
+            self.ctx.lib.spkdiar_gw_multi_end(self.h)
+        self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 class FeaturePack(Features):
@@ -473,6 +539,9 @@ class FeatureView(object):
 
     def gw_run_multi(self, seg_a, seg_b, runs, max_groups=0):
         return self.pack.gw_run_multi(self._sh(seg_a), self._sh(seg_b), runs, max_groups)
+
+    def gw_multi_begin(self, seg_a, seg_b, runs, max_groups=0):
+        return self.pack.gw_multi_begin(self._sh(seg_a), self._sh(seg_b), runs, max_groups)
 
     def cluster(self, seg_a, seg_b, metric, lambdac=1.3):
         return self.pack.cluster(self._sh(seg_a), self._sh(seg_b), metric, lambdac)

@@ -479,39 +479,47 @@ class Detector(object):
         log(p2line('Total detected speaker changes:', st.total_segments))
 
 
-def detect_changes_multi(detectors, recipe, outfs, loader):
+def detect_changes_multi(detectors, recipe, outfs, loader, after=None):
     """Several detectors (e.g. -d BIC, -d GLR and -d KL2 with otherwise the script's flags) over
     the SAME recipe and resident features: the growing-window searches of all of them run side
-    by side on the GPU (``spkdiar_gw_run_multi``), then every detector replays its own records
-    exactly as ``detect_changes`` does.  Outputs are identical to calling ``detect_changes`` on
-    each detector in turn."""
+    by side on the GPU (``spkdiar_gw_multi_*``), and every detector replays its own records
+    exactly as ``detect_changes`` does, in the order given.  Outputs are identical to calling
+    ``detect_changes`` on each detector in turn.
+
+    ``after``: ``{k: fn}`` - ``fn(detector, where)`` is called as soon as detector k has written
+    its output, while the searches of the later detectors are still running on their own SMs;
+    ``where`` = (stream, sms) the search of detector k ran on, or None (so that e.g. the
+    clustering of its turns can be queued there: ``Context.exec_on``)."""
+    after = after or {}
     dets = [d for d in detectors if d.method == 'gw' and not d.tt and d.gw_on_device]
-    if len(dets) >= 2 and len({d.rate for d in dets}) == 1:
-        groups = []
-        this_wav = this_lna = ''
-        feat = None
-        chains = []
-        for line in recipe:                                  # the walk of detect_changes (CD:360-374)
-            if line.audio != this_wav:
-                if chains:
-                    groups.append((feat, chains))
-                    chains = []
-                this_wav = line.audio
-                feat = loader(line)
-            if line.lna != this_lna:
-                this_lna = line.lna
-                chains.append(dets[0]._bounds(line, feat.n))
-        if chains:
-            groups.append((feat, chains))
-        for feat, ch in groups:
-            seg_a = [c[0] for c in ch]
-            seg_b = [c[1] for c in ch]
+    handles = []
+    try:
+        last = None
+        if len(dets) >= 2 and len({d.rate for d in dets}) == 1:
+            groups = dets[0].gw_chains(recipe, loader)
             runs = [dict(rate=d.rate, winsize=d.winsize, winstep=d.winstep, deltaws=d.deltaws,
                          threshold=d.threshold, lambdac=d.lambdac, metric=d.metric) for d in dets]
-            for d, r in zip(dets, feat.gw_run_multi(seg_a, seg_b, runs)):
-                d._prefetch[(id(feat), tuple(seg_a), tuple(seg_b))] = r
-    for d, outf in zip(detectors, outfs):
-        d.detect_changes(recipe, outf, loader=loader)
+            for g, (feat, ch) in enumerate(groups):
+                h = feat.gw_multi_begin([c[0] for c in ch], [c[1] for c in ch], runs)
+                handles.append((feat, ch, h))
+                if g + 1 < len(groups):              # one asynchronous object per context: finish this wav first
+                    for k, d in enumerate(dets):
+                        d.prefetch(feat, ch, h.wait(k))
+                    h.close()
+                else:
+                    last = (feat, ch, h)
+        for k, (d, outf) in enumerate(zip(detectors, outfs)):
+            where = None
+            if last is not None and d in dets:
+                feat, ch, h = last
+                d.prefetch(feat, ch, h.wait(dets.index(d)))
+                where = h.where(dets.index(d))
+            d.detect_changes(recipe, outf, loader=loader)
+            if k in after:
+                after[k](d, where)
+    finally:
+        for _, _, h in handles:
+            h.close()
 
 
 def build_parser():

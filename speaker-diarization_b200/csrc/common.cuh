@@ -40,6 +40,10 @@ struct spkdiar_ctx {
     cudaStream_t aux[SPKDIAR_MAX_RUNS] = {nullptr};
     cudaEvent_t aux_done[SPKDIAR_MAX_RUNS] = {nullptr};
     int naux = 0;
+    // spkdiar_ctx_exec: calls run on another stream / with an SM limit (queued behind an asynchronous search)
+    cudaStream_t base_stream = nullptr;
+    int sms_limit = 0;
+    bool gw_busy = false;         // an asynchronous search object is open
 };
 
 struct spkdiar_feat {

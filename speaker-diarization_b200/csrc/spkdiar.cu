@@ -28,7 +28,7 @@ static thread_local char g_create_err[512] = "";
 
 static int grid_for(const spkdiar_ctx* c, int64_t tasks, int per_cta, int ctas_per_sm) {
     int64_t want = (tasks + per_cta - 1) / per_cta;
-    int64_t cap = (int64_t)c->sms * ctas_per_sm;
+    int64_t cap = (int64_t)(c->sms_limit > 0 ? std::min(c->sms, c->sms_limit) : c->sms) * ctas_per_sm;
     if (want < 1) want = 1;
     return (int)(want < cap ? want : cap);
 }

@@ -96,3 +96,42 @@ def test_split_declines_inexact_rates(ctx):
         with env(SPKDIAR_GW_MINLEN=4):
             auto = feat.gw_run([0], [20000], *args)
     _same(plain, auto)
+
+
+def test_async_searches_with_clustering_queued_behind_the_first(ctx):
+    """begin / wait / exec_on: the BIC search is collected first and its turns are clustered on the
+    stream and SMs it ran on while the KL2 chain is still running; everything equals the
+    synchronous calls."""
+    rec = synth.make_recording(1500, 60000, 6)
+    runs = [dict(rate=100.0, winsize=100.0, winstep=300.0, deltaws=10.0, threshold=t, lambdac=1.0, metric=m)
+            for m, t in ((_abi.BIC, 0.0), (_abi.GLR, 1500.0), (_abi.KL2, 4000.0))]
+
+    def turns(win):
+        cuts = [0] + [int(r['start'] + r['maxi_fine']) for r in win if r['positive']] + [60000]
+        return cuts[:-1], cuts[1:]
+    with ctx.upload(rec.frames) as feat:
+        want = feat.gw_run_multi([0], [60000], runs)
+        sa, sb = turns(want[0][0])
+        with feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
+            want_merges, want_stats = cl.run(0.0, 0, 1)
+        with feat.gw_multi_begin([0], [60000], runs) as h:
+            bic = h.wait(0)
+            stream, sms = h.where(0)
+            assert stream and 0 < sms < ctx.sm_count
+            ctx.exec_on(stream, sms)
+            try:
+                with feat.cluster(*turns(bic[0]), _abi.BIC, 1.3) as cl:
+                    merges, stats = cl.run(0.0, 0, 1)
+            finally:
+                ctx.exec_on()
+            kl2 = h.wait(2)                      # out of order on purpose
+            glr = h.wait(1)
+            with pytest.raises(_abi.SpkdiarError):
+                h.wait(1)                        # collected already
+        for w, g in zip(want, (bic, glr, kl2)):
+            _same(w, g)
+        assert np.array_equal(merges, want_merges) and np.array_equal(stats, want_stats)
+        # an object that is closed without being collected, and a second one right after it
+        feat.gw_multi_begin([0], [60000], runs[:2]).close()
+        with feat.gw_multi_begin([0], [60000], runs[:1]) as h:
+            _same(want[0], h.wait(0))
