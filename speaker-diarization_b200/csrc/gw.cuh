@@ -741,7 +741,9 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                             int w = 0;
                             while (id >= plan.sec[w + 1]) ++w;
                             const int r = id - plan.sec[w];
-                            const int k = r / rterms, sub = r - k * rterms;
+                            // GLR: first the right terms of all offsets, then the (more expensive) mix terms, so
+                            // that the warps of a round work on the same kind of term
+                            const int sub = r >= plan.K[w] ? 1 : 0, k = r - sub * plan.K[w];
                             mm = base + (int64_t)(start + gw_T(g, k));
                             ee = base + (int64_t)plan.e[w];
                             term = sub == 0 ? 1 : 2;
