@@ -158,3 +158,22 @@ def test_overlapped_batches_equal_batches(ctx):
     assert got == want
     assert list(corpus.diarize_batches(ctx, [], 100)) == []
     assert list(corpus.diarize_batches(ctx, batches[:1], 100)) == want[:1]
+
+
+def test_run_corpus_batched_equals_one_at_a_time(tmp_path):
+    """The corpus driver: device batches, with and without the overlapped pipeline, write the
+    files the one-recording-at-a-time driver writes."""
+    items = []
+    for k in range(7):
+        rec = synth.make_recording(980 + k, 4000 + 300 * k, 2 + k % 3, turn_lo=3, turn_hi=9)
+        items.append(('r%d' % k, synth.one_line_recipe('/syn/r%d.wav' % k, rec), rec.frames))
+    outs = {}
+    for name, kw in (('single', {}), ('batch', dict(batch=3)), ('overlap', dict(batch=3, overlap=True))):
+        d = tmp_path / name
+        outs[name] = corpus.run_corpus(items, outdir=str(d), frame_rate=100, device=0, **kw)
+    assert outs['single'] == outs['batch'] == outs['overlap'] and len(outs['single']) == 7
+    for k in range(7):
+        for ext in ('.recipe', '.spkc.recipe'):
+            want = (tmp_path / 'single' / ('r%d%s' % (k, ext))).read_text()
+            assert (tmp_path / 'batch' / ('r%d%s' % (k, ext))).read_text() == want
+            assert (tmp_path / 'overlap' / ('r%d%s' % (k, ext))).read_text() == want
