@@ -51,7 +51,8 @@ namespace spk {
 constexpr int GW_WARPS = 12;
 constexpr int GW_THREADS = GW_WARPS * 32;
 constexpr int GW_BMAX = GW_WARPS;       // windows per speculative batch (one deciding warp each)
-constexpr int GW_JMAX = 128;            // fine-tune candidates (2*istep + 1 <= JMAX)
+constexpr int GW_JMAX = 160;            // fine-tune candidates (2*istep + 1 <= JMAX; fused first wave: every frame
+                                        // a fine tune of window 0 could look at)
 #define GW_NEG_INIT (-9223372036854775808.0)   /* -sys.maxint - 1 as a double, CD:203 */
 
 constexpr int KS = 2 * VS;              // doubles per cached KL2 side: diag(S)[40], diag(S^-1)[40]
@@ -77,6 +78,7 @@ struct GwDev {                 // kernel parameters
     double rate, winsize, winstep, deltaws, threshold, lambda, minfeas, istep;
     int32_t metric;
     int32_t kl2_depth[3];      // KL2 speculation depth of the 1st, 2nd and later coarse waves after a change
+    int32_t fuse_ok;           // KL2: the first wave after a change may carry the fine tune of window 0 (see GwPlan::fuse)
     // workspaces, per group
     double* left;              // [ngroups][kmax]
     double* right;             // [ngroups][2 parity][bmax][kmax][rterms]
@@ -128,6 +130,15 @@ struct GwPlan {                // shared memory, written by thread 0
     int pend_bk;               // coarse maximum of the window waiting for its fine tune
     int left_valid;            // offsets k < left_valid have a cached left term / left side
     int side_next;             // KL2: next unclaimed side task of this CTA's chunk
+    // KL2, FUSED first wave after a change: besides the coarse candidates of the batch the wave scores every
+    // frame a fine tune of WINDOW 0 could look at (fi[q] = frame mlo + q, nJ = their number), so that a change
+    // found in window 0 - 93 % of the changes of the reference's KL2 on the 1-hour bench recording - is fine
+    // tuned by the deciding warp from values already there and needs no fine wave of its own
+    int fuse;
+    int nJ0;                   // fine candidates per coarse maximum (CD:235-251)
+    long long mlo;             // chain-relative frame of fi[0]
+    double fbd;                // best fine candidate of window 0 (strictly above nothing yet: GW_NEG_INIT)
+    int fbj, fninf;
     double start;              // window start of the chain (fp64, chain-relative)
     double pl[GW_BMAX];        // BIC: pooled term of window w
     // KL2 sum chains that survive from the previous coarse wave of the same `start`
@@ -367,11 +378,11 @@ __device__ __forceinline__ void gw_sum_round(const GwChainCtx& c, const GwChain&
 
 // chain ct of the current wave (see the kinds above)
 __device__ __forceinline__ GwChain gw_make_chain(const GwChainCtx& c, int ct, int nright, int left_valid,
-                                                 int64_t s0) {
+                                                 int64_t s0, bool fine) {
     const GwDev& g = *c.g;
     const GwPlan& plan = *c.plan;
     GwChain ch;
-    if (plan.mode == 0 && ct < nright) {                   // coarse right chain of offset k
+    if (!fine && ct < nright) {                            // coarse right chain of offset k
         const int k = ct;
         ch.kind = 0; ch.a = k;
         int w0 = 0;
@@ -384,7 +395,7 @@ __device__ __forceinline__ GwChain gw_make_chain(const GwChainCtx& c, int ct, in
             ch.pos = c.base + (int64_t)(c.start + gw_Tp(&g, k));
             ch.init = nullptr;
         }
-    } else if (plan.mode == 0) {                            // coarse left chain
+    } else if (!fine) {                                     // coarse left chain
         ch.kind = 1; ch.a = 0; ch.w0 = 0; ch.nsnap = plan.nL;
         if (plan.k0 > 0) {
             ch.pos = c.base + (int64_t)(c.start + gw_Tp(&g, plan.k0 - 1));
@@ -524,6 +535,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
             int nJ = 0;
             while (i < endtune && nJ < GW_JMAX) { if ((nJ & 31) == lane) plan.fi[nJ] = i; ++nJ; i += 1; }
             if (lane == 0) {
+                plan.fuse = 0;
                 plan.nJ = nJ;
                 plan.nW = 1;
                 plan.e[0] = st.pend_e;
@@ -580,7 +592,27 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
             plan.sec[lane] = off0 + ksc - unit;
             if (lane == nWc - 1) { plan.sec[nWc] = off0 + ksc; plan.ntask = (KL2 ? nL : 0) + off0 + ksc; }
         }
-        if (lane == 0) { plan.nW = nWc; plan.k0 = st.left_valid; plan.nL = nL; plan.kmaxw = kmaxw; }
+        if (lane == 0) { plan.nW = nWc; plan.k0 = st.left_valid; plan.nL = nL; plan.kmaxw = kmaxw; plan.fuse = 0; }
+        if (KL2 && g.fuse_ok && st.coarse_waves == 0 && st.left_valid == 0) {
+            const int K0 = __shfl_sync(0xffffffffu, Kw, 0);
+            int nJ0 = 0;                                                    // CD:235-251 for the first offset
+            for (double i = gw_T(g, 0) - g.istep; i < gw_T(g, 0) + g.istep && nJ0 < GW_JMAX; i += 1) ++nJ0;
+            if (K0 > 0 && nJ0 > 0) {
+                const double lo = gw_T(g, 0) - g.istep;
+                const double hi = (gw_T(g, K0 - 1) - g.istep) + (double)(nJ0 - 1);
+                const long long mlo = (long long)(st.start + lo), mhi = (long long)(st.start + hi);
+                const long long nQ = mhi - mlo + 1;
+                const long long e0 = (long long)__shfl_sync(0xffffffffu, my_e, 0);
+                if (nQ <= GW_JMAX && mlo > (long long)st.start && mhi < e0) {
+                    for (int q = lane; q < (int)nQ; q += 32) plan.fi[q] = (double)(mlo + q) - st.start;
+                    __syncwarp();
+                    if (lane == 0) {
+                        plan.fuse = 1; plan.nJ = (int)nQ; plan.nJ0 = nJ0; plan.mlo = mlo; plan.pend_bk = 0;
+                        plan.ntask += 2 * (int)nQ;
+                    }
+                }
+            }
+        }
     };
     // claim `cnt` consecutive output slots (warp 0; every lane keeps the same cursor)
     auto claim_slots = [&](int cnt) -> unsigned long long {
@@ -630,13 +662,49 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     const int cw = warp - GW_CHAIN_WARP0;
                     const int nright = plan.mode == 0 ? plan.kmaxw : plan.nJ;
                     const int nct = nright + ((plan.mode == 0 ? plan.nL : plan.nJ) > 0 ? 1 : 0);
-                    for (int c0 = rank; c0 < nct; c0 += g.group_ctas * GW_CHAIN_WARPS) {
+                    // a fused wave also runs the chains of a fine wave over fi[]: nJ right chains and the left one
+                    const int nctf = (plan.mode == 0 && plan.fuse) ? plan.nJ + 1 : 0;
+                    for (int c0 = rank; c0 < nct + nctf; c0 += g.group_ctas * GW_CHAIN_WARPS) {
                         const int ct = c0 + cw * g.group_ctas;
                         GwChain ch;
                         ch.kind = 0; ch.a = 0; ch.w0 = 0; ch.nsnap = 0; ch.pos = 0; ch.init = nullptr;
-                        if (ct < nct) ch = gw_make_chain(cc, ct, nright, left_valid, s0);
-                        gw_sum_round(cc, ch, ct < nct && ch.nsnap > 0, range, ring, ring_bar, ring_phase, cw, lane,
-                                     n_rows, t_wait);
+                        if (ct < nct) ch = gw_make_chain(cc, ct, nright, left_valid, s0, plan.mode != 0);
+                        else if (ct < nct + nctf - 1) ch = gw_make_chain(cc, ct - nct, plan.nJ, left_valid, s0, true);
+                        if (nctf > 0 && ct == nct + nctf - 1) {
+                            // The left sums of a fused wave: ONE running sum from the window start with a snapshot at
+                            // EVERY frame from fi[0] on.  A snapshot per row is the worst case of the ring machinery
+                            // (measured 900 cycles per snapshot), so this chain reads its rows straight from global
+                            // memory, sixteen loads in flight, and stores the running sum after every row.
+                            const float* row = g.x + s0 * D39 + lane;
+                            const bool second = lane + 32 < D39;
+                            const int nrow = (int)(plan.mlo - (long long)start) + plan.nJ - 1;     // rows s0 .. last fine frame
+                            const int first = (int)(plan.mlo - (long long)start);                  // snapshot q after `first + q` rows
+                            float* dst = ksum_fine + ((int64_t)(parity * 2 + 0) * GW_JMAX) * VS;
+                            float a0 = 0.f, a1 = 0.f;
+                            for (int r0 = 0; r0 < nrow; r0 += 16) {
+                                float u[16], v[16];
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) {
+                                    const bool ok = r0 + q < nrow;
+                                    u[q] = ok ? __ldg(row + (int64_t)(r0 + q) * D39) : 0.f;
+                                    v[q] = (ok && second) ? __ldg(row + (int64_t)(r0 + q) * D39 + 32) : 0.f;
+                                }
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) {
+                                    if (r0 + q < nrow) {
+                                        a0 = __fadd_rn(a0, u[q]); a1 = __fadd_rn(a1, v[q]);
+                                        const int sq = r0 + q + 1 - first;                          // rows summed so far = first + sq
+                                        if (sq >= 0 && sq < plan.nJ) {
+                                            dst[(int64_t)sq * VS + lane] = a0;
+                                            if (second) dst[(int64_t)sq * VS + lane + 32] = a1;
+                                        }
+                                    }
+                                }
+                            }
+                            n_rows += nrow;
+                        }
+                        gw_sum_round(cc, ch, ct < nct + nctf - (nctf > 0 ? 1 : 0) && ch.nsnap > 0, range, ring, ring_bar, ring_phase,
+                                     cw, lane, n_rows, t_wait);
                     }
                     if (cw == 0) { t_chain += clock64() - k0c; t_last_chain = clock64() - k0c; }
                     if (g.trace && n_wave == 1 && lane == 0) g.trace[8 * 4096 + 16 * blockIdx.x + 12 + cw] = clock64() - k0c;
@@ -656,7 +724,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                         if (id >= id_end) break;
                         int64_t ra, rb;
                         double* dst;
-                        if (plan.mode == 0) {
+                        const int ntask0 = plan.mode == 0 ? plan.nL + plan.sec[plan.nW] : 0;    // the rest: fine sides
+                        if (id < ntask0) {
                             if (id < plan.nL) {                                 // left side of a new offset
                                 const int k = plan.k0 + id;
                                 ra = s0; rb = base + (int64_t)(start + gw_T(g, k));
@@ -671,7 +740,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                                 dst = kside_right + ((int64_t)parity * g.kcap + t) * KS;
                             }
                         } else {
-                            const int side = id >= plan.nJ ? 1 : 0, j = id - side * plan.nJ;
+                            const int idf = id - ntask0;
+                            const int side = idf >= plan.nJ ? 1 : 0, j = idf - side * plan.nJ;
                             const int64_t mm = base + (int64_t)(start + plan.fi[j]);
                             ra = side ? mm : s0;
                             rb = side ? base + (int64_t)plan.e[0] : mm;
@@ -691,10 +761,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     tr[4] = k1c - k0c; tr[5] = clock64() - k1c; tr[6] = (long long)(plan.e[plan.nW - 1] - start); tr[7] = t_last_chain;
                 }
                 // ---- distances: one warp per candidate ----
-                const int ncand = plan.mode == 0 ? plan.sec[plan.nW] : plan.nJ;
-                for (int t = warp * g.group_ctas + rank; t < ncand; t += gwarps) {
+                const int ncand0 = plan.mode == 0 ? plan.sec[plan.nW] : 0;               // the rest: fine candidates
+                const int ncand = ncand0 + ((plan.mode != 0 || plan.fuse) ? plan.nJ : 0);
+                for (int tt = warp * g.group_ctas + rank; tt < ncand; tt += gwarps) {
                     const double *sl, *sr; const float *ml, *mr; int64_t mm, ee; double* dst;
-                    if (plan.mode == 0) {
+                    const int t = tt < ncand0 ? tt : tt - ncand0;
+                    if (tt < ncand0) {
                         int w = 0;
                         while (t >= plan.sec[w + 1]) ++w;
                         const int k = t - plan.sec[w];
@@ -825,12 +897,32 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     if (ok >= 0 && (bk < 0 || od > bd || (od == bd && ok < bk))) { bd = od; bk = ok; }
                 }
                 if (lane == 0) { plan.bd[w] = bd; plan.bk[w] = bk; plan.ninf[w] = ninf; plan.pl[w] = pl; }
+                if (KL2 && coarse && w == 0 && plan.fuse && bk >= 0 && bd > g.threshold) {
+                    // fused wave, window 0 is positive: its fine tune (CD:235-251) over the dense values
+                    const double i0 = gw_T(g, bk) - g.istep;
+                    double fd = GW_NEG_INIT; int fj = -1; int fninf = 0;
+                    for (int j = lane; j < plan.nJ0; j += 32) {
+                        const long long m = (long long)(start + (i0 + (double)j));
+                        const double d = __ldcg(f0 + (m - plan.mlo));
+                        if (d == d_inf() || d == -d_inf()) ++fninf;
+                        else if (d > fd) { fd = d; fj = j; }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double od = __shfl_xor_sync(0xffffffffu, fd, o);
+                        const int oj = __shfl_xor_sync(0xffffffffu, fj, o);
+                        fninf += __shfl_xor_sync(0xffffffffu, fninf, o);
+                        if (oj >= 0 && (fj < 0 || od > fd || (od == fd && oj < fj))) { fd = od; fj = oj; }
+                    }
+                    if (lane == 0) { plan.fbd = fd; plan.fbj = fj; plan.fninf = fninf; }
+                }
             }
             __syncthreads();
             const long long c4 = clock64();
 
             // ================= warp 0: apply the reference's decision rules, plan the next wave =================
             if (warp == 0) {
+                bool fused_pos = false;            // the change of window 0 was fine tuned inside this (fused) wave
                 if (plan.mode == 0) {
                     // lane w looks at window w; windows count in order up to the first positive one
                     // (it goes to the fine tune) or the first negative one that ends the chain
@@ -877,6 +969,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                         st.pend_ninf = __shfl_sync(0xffffffffu, ninfw, fpos);
                         st.end = st.pend_e;
                         if (lane == fpos) { plan.pend_bk = bk; plan.pend_pl = plw; }
+                        fused_pos = KL2 && plan.fuse && fpos == 0;
                     }
                     if (fin) st.done = true;
                     if (SPLIT && !st.done && !has_pos && st.end >= __ldg(g.stop + 2 * chain + 1)) { st.done = true; reason = 2; }
@@ -890,17 +983,25 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                         plan.chain_parity = parity;
                         plan.chain_row = base + (int64_t)plan.e[nW - 1];
                     }
-                } else {
+                }
+                if (plan.mode != 0 || fused_pos) {
                     // fine-tune decision, CD:237-251: strict improvement over the coarse maximum, first wins
+                    __syncwarp();
                     double maxd = st.pend_maxd, maxi = st.pend_maxi;
-                    if (plan.bk[0] >= 0 && plan.bd[0] > st.pend_maxd) { maxd = plan.bd[0]; maxi = plan.fi[plan.bk[0]]; }
+                    const int fbest = fused_pos ? plan.fbj : plan.bk[0];
+                    const double fbd = fused_pos ? plan.fbd : plan.bd[0];
+                    const int fninf = fused_pos ? plan.fninf : plan.ninf[0];
+                    if (fbest >= 0 && fbd > st.pend_maxd) {
+                        maxd = fbd;
+                        maxi = fused_pos ? (st.pend_maxi - g.istep) + (double)fbest : plan.fi[fbest];
+                    }
                     if (rank == 0) {
                         const unsigned long long sb = claim_slots(1);
                         if (lane == 0 && (int64_t)sb < g.win_cap) {
                             spkdiar_gw_window r;
                             r.start = st.start; r.end = st.pend_e; r.maxi = st.pend_maxi; r.maxd = st.pend_maxd;
                             r.maxi_fine = maxi; r.maxd_fine = maxd; r.positive = 1; r.chain = chain;
-                            r.ncand = st.pend_ncand; r.ninf = st.pend_ninf + plan.ninf[0]; r.seq = st.seq; r.pad = 0;
+                            r.ncand = st.pend_ncand; r.ninf = st.pend_ninf + fninf; r.seq = st.seq; r.pad = 0;
                             g.win[sb] = r;
                         }
                     }

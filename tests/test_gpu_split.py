@@ -135,3 +135,27 @@ def test_async_searches_with_clustering_queued_behind_the_first(ctx):
         feat.gw_multi_begin([0], [60000], runs[:2]).close()
         with feat.gw_multi_begin([0], [60000], runs[:1]) as h:
             _same(want[0], h.wait(0))
+
+
+@pytest.mark.parametrize('rate,thr', [(100, 4000.0), (100, 400.0), (125, 60.0), (125, 1.0), (100, 1e9)])
+def test_kl2_fused_first_wave_equals_separate_fine_wave(ctx, rate, thr):
+    """KL2: the first wave after a change also scores every frame a fine tune of window 0 could look
+    at, so that a change found in window 0 needs no fine wave.  The records must be those of the
+    search with separate fine waves (SPKDIAR_GW_NOFUSE), bit for bit - also at 125 fps (half-frame
+    positions), with low thresholds (nearly every window 0 fires) and with none firing at all."""
+    rec = synth.make_recording(1600 + rate, 30000, 5, rate=rate)
+    n = rec.frames.shape[0]
+    seg_a, seg_b = [0, 20001], [20000, n]
+    args = (float(rate), float(rate), 3.0 * rate, float(rate // 10), thr, 1.0, _abi.KL2)
+    with ctx.upload(rec.frames) as feat:
+        fused = feat.gw_run(seg_a, seg_b, *args)
+        with env(SPKDIAR_GW_NOFUSE=1):
+            plain = feat.gw_run(seg_a, seg_b, *args)
+        one_cta = feat.gw_run(seg_a * 80, seg_b * 80, *args)         # 160 chains: one CTA each, no speculation
+    _same(plain, fused)
+    if thr <= 400.0:
+        assert plain[0]['positive'].sum() > 5
+    k = len(fused[0])
+    assert len(one_cta[0]) == 80 * k
+    for name in ('start', 'end', 'maxi', 'maxd', 'maxi_fine', 'maxd_fine', 'positive', 'ncand', 'ninf', 'seq'):
+        assert np.array_equal(one_cta[0][name][:k], fused[0][name]), name
