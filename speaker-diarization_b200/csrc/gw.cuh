@@ -664,8 +664,10 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
                     const int nct = nright + ((plan.mode == 0 ? plan.nL : plan.nJ) > 0 ? 1 : 0);
                     // a fused wave also runs the chains of a fine wave over fi[]: nJ right chains and the left one
                     const int nctf = (plan.mode == 0 && plan.fuse) ? plan.nJ + 1 : 0;
-                    for (int c0 = rank; c0 < nct + nctf; c0 += g.group_ctas * GW_CHAIN_WARPS) {
-                        const int ct = c0 + cw * g.group_ctas;
+                    // four NEIGHBOURING chains per CTA (one per chain warp): their row ranges nearly coincide, so
+                    // the one stream of rows the CTA's ring carries serves all four
+                    for (int c0 = rank * GW_CHAIN_WARPS; c0 < nct + nctf; c0 += g.group_ctas * GW_CHAIN_WARPS) {
+                        const int ct = c0 + cw;
                         GwChain ch;
                         ch.kind = 0; ch.a = 0; ch.w0 = 0; ch.nsnap = 0; ch.pos = 0; ch.init = nullptr;
                         if (ct < nct) ch = gw_make_chain(cc, ct, nright, left_valid, s0, plan.mode != 0);
