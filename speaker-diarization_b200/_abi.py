@@ -420,6 +420,8 @@ class GwMulti(object):
 
     def wait(self, r):
         """-> (window records, win_first) of search r, as ``Features.gw_run`` returns them."""
+        if not 0 <= int(r) < len(self.runs):
+            raise SpkdiarError(-2, 'search %d of %d' % (r, len(self.runs)))
         unit = max(float(self.runs[r]['rate']) / 2 - float(self.runs[r]['rate']) / 10, 1.0)
         cap = int(sum(2 * ((b - a) / unit + 2) for a, b in zip(self.seg_a, self.seg_b))) + 16
         first = np.zeros(self.nchain + 1, dtype=np.int64)

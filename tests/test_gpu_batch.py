@@ -177,3 +177,35 @@ def test_run_corpus_batched_equals_one_at_a_time(tmp_path):
             want = (tmp_path / 'single' / ('r%d%s' % (k, ext))).read_text()
             assert (tmp_path / 'batch' / ('r%d%s' % (k, ext))).read_text() == want
             assert (tmp_path / 'overlap' / ('r%d%s' % (k, ext))).read_text() == want
+
+
+def test_argument_errors_of_the_batch_and_async_entry_points(ctx):
+    rec = synth.make_recording(990, 3000, 2)
+    with pytest.raises(_abi.SpkdiarError) as e:
+        ctx.upload_batch([np.zeros((10, 20), dtype=np.float32)])              # not 39-dimensional
+    assert e.value.code == -5
+    with pytest.raises(_abi.SpkdiarError):
+        ctx.upload_batch([])                                                  # an empty batch
+    pack = ctx.upload_batch([rec.frames, rec.frames[:500]])
+    with pytest.raises(_abi.SpkdiarError) as e:
+        pack.cluster_batch([[(0, 100)], []], _abi.BIC)                        # a problem without segments
+    assert e.value.code == -2
+    with pytest.raises(_abi.SpkdiarError) as e:
+        pack.cluster_batch([[(0, 100), (100, 200)]], _abi.KL2)                # KL2 is not in the engines
+    assert e.value.code == -5
+    with pytest.raises(_abi.SpkdiarError) as e:
+        pack.cluster_batch([[(0, 10 ** 9)]], _abi.BIC)                        # outside the packed matrix
+    assert e.value.code == -2
+    runs = [dict(rate=100.0, winsize=100.0, winstep=300.0, deltaws=10.0, threshold=0.0, lambdac=1.0, metric=_abi.BIC)]
+    h = pack.gw_multi_begin([0], [3000], runs)
+    try:
+        with pytest.raises(_abi.SpkdiarError):
+            pack.gw_multi_begin([0], [3000], runs)                            # one asynchronous object per context
+        with pytest.raises(_abi.SpkdiarError):
+            h.wait(1)                                                         # no such search
+        win, first = h.wait(0)
+        assert len(win) > 0
+    finally:
+        h.close()
+    pack.gw_multi_begin([0], [3000], runs).close()                            # and it can be opened again
+    pack.close()
