@@ -182,16 +182,27 @@ class Detector(object):
         maxds, maxd_f, maxi_f, starts = (recs['maxd'].tolist(), recs['maxd_fine'].tolist(),
                                          recs['maxi_fine'].tolist(), recs['start'].tolist())
         self.windows_visited += len(ninf)
+        inf = np.inf
+        # RunStats.window (CD:223-229) inlined: this loop runs once per window of the corpus
+        tdist, twin, dmax, dmin = st.total_dist, st.total_windows, st.max_dist, st.min_dist
         for i in range(len(ninf)):
             if ninf[i] > 0:
                 self._gw_inf_lines(feat, a, recs[i])
-            st.window(maxds[i] if ncand[i] >= 0 else NEG_INIT)
+            d = maxds[i] if ncand[i] >= 0 else NEG_INIT
+            if d != inf and d != -inf:
+                tdist += d
+                twin += 1
+                if d > dmax:
+                    dmax = d
+                if d < dmin:
+                    dmin = d
             if pos[i]:
                 maxi = maxi_f[i]
                 start = starts[i]
                 self.writer.write(line, start, start + maxi, line.start, 'spk_turn', outf, segf)
                 st.detected(maxd_f[i])
                 start += maxi
+        st.total_dist, st.total_windows, st.max_dist, st.min_dist = tdist, twin, dmax, dmin
         end = (line.end - line.start) * self.rate                 # CD:287
         self.writer.write(line, start, end, line.start, 'spk_turn', outf, segf)
 

@@ -87,9 +87,11 @@ class Clusterer(object):
     @staticmethod
     def _range(turn, n):
         """``features[int(s):int(e)]`` (CL1:47, CL2:48) as a clamped range."""
-        a = min(max(int(turn[0]), 0), n)
-        b = min(max(int(turn[1]), 0), n)
-        return (a, max(a, b))
+        a = int(turn[0])
+        b = int(turn[1])
+        a = 0 if a < 0 else (n if a > n else a)
+        b = 0 if b < 0 else (n if b > n else b)
+        return (a, b if b > a else a)
 
     def _ranges(self, spk, n):
         return [self._range(t, n) for t in spk]

@@ -79,6 +79,7 @@ class _BatchJob(object):
     def stage_b(self):
         from . import clustering as pcl
         self.seg_lines = []
+        self.seg_records = []
         for r, (det, rec, v) in enumerate(zip(self.dets, self.parsed, self.views)):
             win, first = self.gw[r]
             c0 = 0
@@ -89,11 +90,16 @@ class _BatchJob(object):
                 det.prefetch(feat, ch, (sub, first[c0:c0 + len(ch) + 1] - first[c0]))
                 c0 += len(ch)
             seg = io.StringIO()
+            det.writer.record = []
             det.detect_changes(rec, seg, loader=lambda l, v=v: v)
             self.seg_lines.append(seg.getvalue().splitlines(True))
+            self.seg_records.append(det.writer.record)
         self.cls = [pcl.Clusterer(self.rate, variant=1, threshold=self.threshold, ctx=self.ctx, **D2_CLUSTER)
                     for _ in self.batch]
-        self.seg_parsed = [recipe_mod.parse(lines) for lines in self.seg_lines]
+        # the clustering stage reads the segmentation RECIPE (text, times rounded to 12 digits): the same
+        # values without the regular-expression searches
+        self.seg_parsed = [recipe_mod.lines_from_records(recs, lines)
+                           for recs, lines in zip(self.seg_records, self.seg_lines)]
         self.problems = [cl.initial_segments(rec, v.n)
                          for cl, rec, v in zip(self.cls, self.seg_parsed, self.views)]
         self.live = [r for r, p in enumerate(self.problems) if p]

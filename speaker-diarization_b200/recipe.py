@@ -20,6 +20,7 @@ _LNA = re.compile(r'lna=(\S+)')
 # character, digit(s) - "5" alone does not match and the line is reported
 _START = re.compile(r'start-time=(\d+.\d+)')
 _END = re.compile(r'end-time=(\d+.\d+)')
+_CANON = re.compile(r'audio=(\S+) lna=(\S+) start-time=(\d+.\d+) end-time=(\d+.\d+)')
 
 
 def parse(lines, report=None):
@@ -27,6 +28,14 @@ def parse(lines, report=None):
     ``report`` (the two messages the reference prints) and skipped."""
     out = []
     for text in lines:
+        # Fast path for lines in the writers' own field order: one match instead of four searches - taken
+        # only when every key's FIRST occurrence is the one the match used, i.e. when the four independent
+        # searches of the reference would return the same groups (a path such as /x/lna=y.wav falls through).
+        m = _CANON.match(text)
+        if m is not None and text.find('lna=') == m.start(2) - 4 and text.find('start-time=') == m.start(3) - 11 \
+                and text.find('end-time=') == m.start(4) - 9:
+            out.append(Line(m.group(1), m.group(2), float(m.group(3)), float(m.group(4))))
+            continue
         ma, ml, ms, me = (_AUDIO.search(text), _LNA.search(text), _START.search(text),
                           _END.search(text))
         # the reference evaluates the fields in this order and gives up at the
@@ -37,6 +46,25 @@ def parse(lines, report=None):
                 report(text)
             continue
         out.append(Line(ma.group(1), ml.group(1), float(ms.group(1)), float(me.group(1))))
+    return out
+
+
+_TIME = re.compile(r'\d+.\d+')
+
+
+def lines_from_records(records, texts):
+    """What ``parse(texts)`` returns, from the fields a ``Writer`` recorded while it wrote those
+    lines (``Writer.record``) - without the regular-expression searches.  A time whose text the
+    reference's pattern would not take whole (an exponent, a sign: ``\\d+.\\d+`` with its unescaped
+    dot) sends that line through ``parse``, so the result is the same in every case."""
+    out = []
+    for rec, text in zip(records, texts):
+        audio, lna, t0, t1 = rec
+        if _TIME.fullmatch(t0) and _TIME.fullmatch(t1) and 'lna=' not in audio and 'start-time=' not in audio \
+                and 'end-time=' not in audio and 'start-time=' not in lna and 'end-time=' not in lna:
+            out.append(Line(audio, lna, float(t0), float(t1)))
+        else:
+            out.extend(parse([text]))
     return out
 
 
@@ -53,6 +81,7 @@ class Writer(object):
         self.segprefix = segprefix
         self.letter = 'a'
         self.count = 0
+        self.record = None          # a list: every written line is also kept as (audio, lna, t0 text, t1 text)
 
     def _lna(self, lna):
         if not self.rename:
@@ -72,6 +101,8 @@ class Writer(object):
         t1 = fstr(end / self.rate + lna_start)
         outf.write('audio=%s lna=%s start-time=%s end-time=%s speaker=%s\n'
                    % (line.audio, lna, t0, t1, tag))
+        if self.record is not None:
+            self.record.append((line.audio, lna, t0, t1))
         if self.segprefix and segf is not None:
             segf.write('audio=%s alignment=%s%s.seg lna=%s start-time=%s end-time=%s speaker=%s\n'
                        % (line.audio, self.segprefix, lna, lna, t0, t1, tag))

@@ -222,3 +222,28 @@ def test_clus_performance_run_length_equals_per_millisecond_lists():
         want[(a, b)] = want.get((a, b), 0) + 1
     got = scoring._co_occurrence(scoring._label_runs(base[0][1], 0.001), scoring._label_runs(prop[0][1], 0.001))
     assert got == want and list(got) == list(want)
+
+
+def test_lines_from_records_equal_parse():
+    """The corpus driver skips the regular expressions when it reads back a recipe it has just
+    written; every case the reference's patterns treat specially must fall back to them."""
+    import io
+    from spkdiar import recipe
+    w = recipe.Writer(100.0)
+    w.record = []
+    out = io.StringIO()
+    src = [recipe.Line('/a/b.wav', 'a_1', 0.0, 10.0), recipe.Line('/a/lna=x.wav', 'a_2', 0.0, 1.0),
+           recipe.Line('/a/c.wav', 'b_7', 0.0, 1.0)]
+    cases = [(0.0, 1234.5), (1e-7, 3.0), (12.3456789012345, 1e17), (-50.0, 20.0), (7.0, 7.0), (1e5 / 3, 2e5 / 3)]
+    for k, (s, e) in enumerate(cases):
+        w.write(src[k % 3], s, e, 0.0 if k % 2 else 1.5, 'spk_turn', out)
+    texts = out.getvalue().splitlines(True)
+    assert len(w.record) == len(texts) == len(cases)
+    assert recipe.lines_from_records(w.record, texts) == recipe.parse(texts)
+    # the fast path of parse itself: same result as four independent searches
+    odd = ['audio=/x/lna=y.wav lna=a_1 start-time=1.0 end-time=2.0\n',
+           'lna=a_3 audio=/z.wav end-time=9.5 start-time=4.25 speaker=s\n',
+           'audio=/z.wav lna=a_4 start-time=5 end-time=6.0\n',
+           'audio=/z.wav lna=a_5 start-time=1e-05 end-time=6.0\n']
+    got = recipe.parse(odd)
+    assert got == [recipe.Line('/x/lna=y.wav', 'y.wav', 1.0, 2.0), recipe.Line('/z.wav', 'a_3', 4.25, 9.5)]
