@@ -445,9 +445,10 @@ def main():
     ap.add_argument('--workload', default='config2', choices=['config2', 'config3', 'config4', 'config5'],
                     help='config2 is the headline (BASELINE.json configs[1]); the others print their own line')
     ap.add_argument('--segments', type=int, default=8000, help='config5: segments of the long recording')
-    ap.add_argument('--files', type=int, default=16, help='config4: recordings per GPU')
-    ap.add_argument('--batch', type=int, default=0, help='config4: recordings per device batch (0: one at a time)')
-    ap.add_argument('--overlap', action='store_true', help='config4 with --batch: overlap device stages and host replay')
+    ap.add_argument('--files', type=int, default=148, help='config4: recordings per GPU')
+    ap.add_argument('--batch', type=int, default=74, help='config4: recordings per device batch (0: one at a time)')
+    ap.add_argument('--no-overlap', dest='overlap', action='store_false',
+                    help='config4 with --batch: do not overlap device stages and host replay')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
