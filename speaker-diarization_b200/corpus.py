@@ -246,3 +246,72 @@ def run_corpus(items, rank=0, world=1, device=None, outdir=None, frame_rate=125,
     for part in gather(local):
         merged.update(part)
     return merged
+
+
+def items_from_recipes(recipe_paths, feapath, feaext='.fea'):
+    """Corpus items for ``run_corpus`` from recipe files as ``voice-detection2.py`` writes them (one
+    recipe per recording, every line of it naming the same wav): the item is called after the recipe
+    file, the frames are read lazily from ``feapath`` / <wav basename> + ``feaext`` when the
+    recording's batch is uploaded."""
+    from .feacat import feature_file_name, read_features
+    items = []
+    for path in recipe_paths:
+        with open(path, 'r') as f:
+            lines = f.readlines()
+        parsed = recipe_mod.parse(lines)
+        if not parsed:
+            raise ValueError('%s: no recipe line with audio / lna / start-time / end-time' % path)
+        wavs = {l.audio for l in parsed}
+        if len(wavs) != 1:
+            raise ValueError('%s names %d wavs; the corpus driver takes one recording per recipe' % (path, len(wavs)))
+        fea = feature_file_name(parsed[0].audio, feapath, feaext)
+
+        def frames(fea=fea):
+            dim, x = read_features(fea)
+            return x
+        items.append((op.splitext(op.basename(path))[0], lines, frames))
+    return items
+
+
+def main(argv=None):
+    """``spk-diarization-corpus.py recipes... feapath -o outdir``: the two hot-path calls of
+    ``spk-diarization2.py`` (lines 122-128) over many recordings.  Started once, or as one process
+    per GPU under ``torchrun`` (recordings are dealt to the ranks by index, no communication but
+    the final gather of the summaries)."""
+    import argparse
+    ap = argparse.ArgumentParser(description='Speaker-turn segmentation + clustering of a corpus of recordings '
+                                 '(spk-diarization2.py flags), recordings sharded over the GPUs.')
+    ap.add_argument('recipes', nargs='+', help='one speech-turn recipe per recording (voice-detection2.py output)')
+    ap.add_argument('feapath', help='directory of the feacat feature files')
+    ap.add_argument('-o', dest='outdir', required=True, help='directory for <name>.spkc.recipe and <name>.recipe')
+    ap.add_argument('-fe', dest='feaext', default='.fea', help='feature file extension, default ".fea"')
+    ap.add_argument('-f', dest='frame_rate', type=int, default=125, help='frame rate, default 125')
+    ap.add_argument('--batch', type=int, default=64, help='recordings per device batch (0: one at a time)')
+    ap.add_argument('--no-overlap', dest='overlap', action='store_false',
+                    help='do not overlap the device stages of the next batch with the host replay')
+    args = ap.parse_args(argv)
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    gather = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('gloo')           # summaries only: a few hundred bytes per recording
+
+        def gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+    items = items_from_recipes(args.recipes, args.feapath, args.feaext)
+    done = run_corpus(items, rank=rank, world=world, device=local, outdir=args.outdir, frame_rate=args.frame_rate,
+                      gather=gather, batch=args.batch, overlap=args.overlap)
+    if rank == 0:
+        for name in sorted(done):
+            s = done[name]
+            print('%s: %d turns, %d speakers (%d windows, %d merges)'
+                  % (name, s['turns'], s['speakers'], s['windows'], s['merges']))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return done
+

@@ -209,3 +209,25 @@ def test_argument_errors_of_the_batch_and_async_entry_points(ctx):
         h.close()
     pack.gw_multi_begin([0], [3000], runs).close()                            # and it can be opened again
     pack.close()
+
+
+def test_corpus_cli_equals_the_two_scripts(tmp_path, capsys):
+    """scripts/spk-diarization-corpus.py writes, per recording, the files the two drop-in scripts
+    write when spk-diarization2.py calls them one after the other (D2:122-128)."""
+    from conftest import run_product
+    from cases import D2_GW
+    paths = []
+    for k in range(3):
+        rec = synth.make_recording(60 + k, 5000 + 400 * k, 2 + k, turn_lo=3, turn_hi=8)
+        lines = synth.one_line_recipe('/media/c%d.wav' % k, rec)
+        rp, feadir = synth.write_case(str(tmp_path), 'c%d' % k, rec, lines)
+        paths.append(rp)
+    outdir = tmp_path / 'out'
+    done = corpus.main(paths + [feadir, '-o', str(outdir), '-f', '100', '--batch', '2'])
+    assert sorted(done) == ['c0', 'c1', 'c2'] and 'c1: ' in capsys.readouterr().out
+    for k, rp in enumerate(paths):
+        seg, clu = str(tmp_path / ('s%d.recipe' % k)), str(tmp_path / ('k%d.recipe' % k))
+        run_product('cd', 0, [rp, feadir, '-o', seg, '-f', '100'] + D2_GW)
+        run_product('cl', 1, [seg, feadir + '/', '-o', clu, '-f', '100', '-m', 'hi', '-l', '1.3'])
+        assert (outdir / ('c%d.spkc.recipe' % k)).read_text() == open(seg).read()
+        assert (outdir / ('c%d.recipe' % k)).read_text() == open(clu).read()

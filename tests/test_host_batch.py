@@ -107,3 +107,23 @@ def test_shard_and_batches_cover_the_corpus_once():
             assert all(0 < len(p) <= 5 for p in parts)
             seen += [k for p in parts for k in p]
         assert sorted(seen) == list(range(37))
+
+
+def test_items_from_recipes_reads_lazily(tmp_path):
+    from spkdiar import synth
+    fea = tmp_path / 'fea'
+    fea.mkdir()
+    paths = []
+    for k in range(3):
+        rec = synth.make_recording(40 + k, 500 + 10 * k, 2)
+        lines = synth.one_line_recipe('/media/r%d.wav' % k, rec)
+        rp, _ = synth.write_case(str(tmp_path), 'r%d' % k, rec, lines)
+        paths.append(rp)
+    items = corpus.items_from_recipes(paths, str(fea))
+    assert [it[0] for it in items] == ['r0', 'r1', 'r2']
+    assert callable(items[1][2]) and items[1][2]().shape == (510, 39)
+    (tmp_path / 'bad.recipe').write_text('audio=/a.wav lna=a_1 start-time=0.0 end-time=1.0\n'
+                                         'audio=/b.wav lna=b_1 start-time=0.0 end-time=1.0\n')
+    import pytest
+    with pytest.raises(ValueError):
+        corpus.items_from_recipes([str(tmp_path / 'bad.recipe')], str(fea))
