@@ -270,7 +270,9 @@ int  spkdiar_cluster_run_sharded_nccl(spkdiar_clus* c, double threshold, int32_t
                                       spkdiar_merge* out, int64_t cap, int64_t* nmerges,
                                       double* stats4);
 /* The same run as ONE persistent kernel per rank whose ranks exchange their candidates
- * through peer memory (NVLink): every rank owns a mailbox of 2 x nranks 32-byte slots;
+ * through peer memory (NVLink): every rank owns a mailbox of 3 x nranks 32-byte slots
+ * (candidates of even merges, of odd merges, and the final statistics round, which therefore never shares a
+ * slot with the first candidate of the NEXT run on the same mailboxes);
  * per merge, CTA 0 of a rank stores its candidate into its slot of EVERY rank's mailbox
  * (payload, then a sequence number with st.release.sys) and all CTAs poll their own
  * device's mailbox (ld.acquire.sys) - no host round trip, no collective library call.
@@ -301,6 +303,11 @@ int  spkdiar_cluster_free(spkdiar_clus* c);
 /* test hook: copy the current pair matrix (nseg x nseg, row-major, entries of
  * dead rows / columns undefined) and the alive flags to the host */
 int  spkdiar_cluster_matrix(spkdiar_clus* c, double* out, uint8_t* alive);
+/* test hook: the NEXT spkdiar_cluster_run on this handle also copies row `a` of the pair matrix as merge m
+ * rewrote it (nseg doubles, ORIGINAL indices; entries of dead columns undefined) to host_rows[m * nseg ...],
+ * for the first cap_rows merges - what a host needs to replay the agglomeration and check that every merge
+ * was ndarray.argmin of the live matrix (spk-clustering.py:203-205).  cap_rows = 0 switches it off. */
+int  spkdiar_cluster_rowlog(spkdiar_clus* c, double* host_rows, int64_t cap_rows);
 
 #ifdef __cplusplus
 }

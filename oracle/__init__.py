@@ -21,7 +21,7 @@ numpy/scipy (docker/Dockerfile:49).  The oracle is therefore pinned by
 ``/root/reference`` at run time, put through a small documented set of
 py2->py3 token rewrites IN MEMORY (never written to the repo), executed in this
 container, and their recipes / stdout compared with the oracle's
-(``tests/test_oracle_vs_reference.py``, skipped where ``/root/reference`` is
+(``tests/test_oracle.py``, skipped where ``/root/reference`` is
 absent).  The same runs produced the committed fixtures under
 ``tests/golden/`` (generator: ``tests/golden/make_golden.py``; numpy / scipy
 versions recorded inside each fixture).

@@ -179,6 +179,7 @@ class ChangeDetection(object):
         while end <= n:
             i = minfeas
             maxd = -MAXINT - 1
+            second = -MAXINT - 1        # runner-up, for the margin audit only
             maxi = None
             while i < end - start - minfeas:
                 arr1 = features[int(start):int(start + i)]
@@ -189,16 +190,22 @@ class ChangeDetection(object):
                     self.log(py2_print_str('Time:', start / rate + i / rate + lna_start,
                                            '- Distance:', d))
                 if d > maxd and d != np.inf:
+                    second = maxd
                     maxd = d
                     maxi = i
                 elif d == np.inf or d == -np.inf:
                     self.log(py2_print_str('Inf:', arr1.shape, arr2.shape, d))
+                elif d > second:
+                    second = d
                 i += istep
             self._window_stats(maxd)
             rec = None
             if self.trace is not None:
+                # gap: winner minus runner-up of the coarse scan (margin audit of the tests;
+                # not part of the reference's flow)
                 rec = dict(line=recline, start=start, end=end, maxi=maxi,
-                           maxd=float(maxd), positive=False)
+                           maxd=float(maxd), positive=False,
+                           gap=float(maxd) - float(second))
                 self.trace.append(rec)
             if maxd > self.threshold and maxd != np.inf and maxd != -np.inf:
                 i = maxi - istep
@@ -209,13 +216,17 @@ class ChangeDetection(object):
                     arr = features[int(start):int(end)]
                     d = self._dist3(arr1, arr2, arr, i, memo)
                     if d > maxd and d != np.inf:
+                        second = maxd
                         maxd = d
                         maxi = i
                     elif d == np.inf or d == -np.inf:
                         self.log(py2_print_str('Inf:', arr1.shape, arr2.shape, d))
+                    elif d > second and i != maxi:
+                        second = d
                     i += 1
                 if rec is not None:
-                    rec.update(positive=True, maxi_fine=maxi, maxd_fine=float(maxd))
+                    rec.update(positive=True, maxi_fine=maxi, maxd_fine=float(maxd),
+                               gap_fine=float(maxd) - float(second))
                 self.write_recipe_line(recline, start, start + maxi, lna_start,
                                        outf, segf)
                 memo = D.BicMemo()

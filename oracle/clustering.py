@@ -195,7 +195,13 @@ class Clustering(object):
                 self.log(py2_print_str('Merging:', a + 1, 'and', b + 1,
                                        'distance:', mind))
                 if self.trace is not None:
-                    self.trace.append((int(a), int(b), float(mind)))
+                    # 4th entry: distance of the runner-up pair minus the minimum (margin audit of
+                    # the tests; not part of the reference's flow)
+                    flat = distances.ravel().copy()
+                    flat[index] = np.inf
+                    if v1:
+                        flat[b * len(speakers) + a] = np.inf   # the mirror entry of a symmetric matrix
+                    self.trace.append((int(a), int(b), float(mind), float(np.nanmin(flat)) - float(mind)))
                 speakers[a].extend(speakers[b])
                 speakers.pop(b)
                 distances = np.delete(distances, b, 0)

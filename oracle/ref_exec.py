@@ -25,6 +25,9 @@ R7  the loaded feature matrix is viewed as ``_FloatIdx``, an ndarray subclass
     (CD:144-145, 305-306, 309; CL2:48-50, 142)
 R8  (clus-performance / spk-change-performance only) ``izip`` -> ``zip``,
     ``.iteritems()`` -> ``.items()``
+R9  (aku2elan.py only) ``from lxml import etree`` resolves to ``oracle/lxml_shim.py``
+    when lxml is not installed: the reference builds the element tree, the shim
+    serialises it the way lxml does under Python 2
 """
 
 import contextlib
@@ -121,6 +124,14 @@ def run(script, argv, cwd=None):
     old_argv = sys.argv
     old_cwd = os.getcwd()
     sys.argv = [script] + [str(a) for a in argv]
+    shim = 'lxml' not in sys.modules and _lxml_missing()
+    if shim:                                    # R9: see oracle/lxml_shim.py
+        import types
+        from . import lxml_shim
+        pkg = types.ModuleType('lxml')
+        pkg.etree = lxml_shim
+        sys.modules['lxml'] = pkg
+        sys.modules['lxml.etree'] = lxml_shim
     try:
         if cwd:
             os.chdir(cwd)
@@ -131,4 +142,35 @@ def run(script, argv, cwd=None):
     finally:
         sys.argv = old_argv
         os.chdir(old_cwd)
+        if shim:
+            del sys.modules['lxml'], sys.modules['lxml.etree']
     return buf.getvalue(), g
+
+
+def _lxml_missing():
+    import importlib.util
+    return importlib.util.find_spec('lxml') is None
+
+
+class _ParserCaptured(Exception):
+    pass
+
+
+def parser_of(script):
+    """The ``argparse.ArgumentParser`` the reference script builds (its flags, defaults, choices and
+    types): the script is executed up to its ``parse_args()`` call, which is intercepted."""
+    import argparse
+    box = []
+    orig = argparse.ArgumentParser.parse_args
+
+    def grab(self, *a, **k):
+        box.append(self)
+        raise _ParserCaptured()
+    argparse.ArgumentParser.parse_args = grab
+    try:
+        run(script, [])
+    except _ParserCaptured:
+        pass
+    finally:
+        argparse.ArgumentParser.parse_args = orig
+    return box[0]

@@ -1,12 +1,13 @@
 """Timing breakdown of the batched corpus path (run on the GPU box):
-python tests/gpu_batch_time.py [files] [batch]"""
+python profiles/drivers/batch_time.py [files] [batch]"""
+import os
 import sys
 import time
 
 import numpy as np
 import torch
 
-sys.path.insert(0, '.')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import spkdiar                                   # noqa: F401,E402
 from spkdiar import _abi, synth, corpus          # noqa: E402
 

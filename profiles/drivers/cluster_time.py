@@ -1,11 +1,11 @@
 """Timing driver (not a test): agglomerative clustering of BASELINE config 3 (3-hour
 recording, ~2,000 segments) or a prefix of config 5 (argv: nsegments).  SPKDIAR_CL_DEBUG=1
-prints the merge loop's phase counters.  Usage: python tests/gpu_cluster_time.py [c3 | <nseg>] [variant]"""
+prints the merge loop's phase counters.  Usage: python profiles/drivers/cluster_time.py [c3 | <nseg>] [variant]"""
 import hashlib
 import os
 import sys
 import time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import spkdiar                                   # noqa: F401
 from spkdiar import synth, _abi

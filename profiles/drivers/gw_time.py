@@ -1,11 +1,11 @@
 """Timing driver (not a test): the three growing-window passes and the clustering of
 bench config 2 on the 1-hour recording, with the kernel's phase counters
-(SPKDIAR_GW_DEBUG=1).  Usage: python tests/gpu_gw_time.py [BIC GLR KL2 CL]"""
+(SPKDIAR_GW_DEBUG=1).  Usage: python profiles/drivers/gw_time.py [BIC GLR KL2 CL]"""
 import hashlib
 import os
 import sys
 import time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import spkdiar                                   # noqa: F401
 from spkdiar import synth, _abi

@@ -1,5 +1,5 @@
 import sys, os, collections
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import spkdiar
 from spkdiar import synth, _abi
 rec = synth.make_recording(1002, 360000, 8)

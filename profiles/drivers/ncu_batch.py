@@ -2,7 +2,7 @@
 corpus.diarize_batch - packed statistics, one growing-window launch (one CTA per recording),
 one clustering launch (one CTA per recording).  argv[1] = recordings (default 148)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import spkdiar                                   # noqa: F401
 from spkdiar import synth, _abi, corpus
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 148

@@ -1,7 +1,7 @@
 """Small driver for ncu: statistics + one growing-window pass (BIC by default; argv[1] =
 BIC | GLR | KL2) on the 1-hour recording of bench config 2."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import spkdiar                                   # noqa: F401
 from spkdiar import synth, _abi
 name = (sys.argv[1] if len(sys.argv) > 1 else 'BIC').upper()

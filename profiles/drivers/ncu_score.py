@@ -1,6 +1,6 @@
 """Small driver for ncu: frame statistics + one batched BIC scoring call."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import spkdiar
 from spkdiar import synth, _abi

@@ -1,7 +1,7 @@
 """Small driver for compute-sanitizer: the batched corpus path and a split growing-window
 search on small inputs (every new kernel of round 1d launches at least once)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import spkdiar                                   # noqa: F401
 from spkdiar import synth, _abi, corpus
 ctx = _abi.Context(0)

@@ -1,11 +1,11 @@
 """Timing driver (not a test): sharded clustering of a config-5-like recording under torchrun
 (one rank per GPU, NCCL all-gather of the 16-byte candidates) or as a single process.
-Usage: [torchrun --nproc-per-node N] python tests/gpu_sharded_time.py <nsegments>"""
+Usage: [torchrun --nproc-per-node N] python profiles/drivers/sharded_time.py <nsegments>"""
 import hashlib
 import os
 import sys
 import time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import spkdiar                                   # noqa: F401

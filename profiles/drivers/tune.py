@@ -1,7 +1,7 @@
 """Threshold tuning for the GLR / KL2 growing-window passes of bench config 2
 (run once on the GPU; the chosen values are frozen in bench.py)."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import spkdiar
 from spkdiar import synth, _abi

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Drop-in for the reference's ./spk-change-detection.py (same flags, recipe in / recipe out,
-same stdout text); the numeric work runs on the GPU through libspkdiar.so."""
+"""Drop-in for the reference's ./aku2elan.py (same flags, same files in and out, same stdout
+text); host-only text glue around the hot path (speaker-diarization_b200/glue.py)."""
 import os
 import sys
 
@@ -8,5 +8,5 @@ import sys
 # e.g. inside a checkout of the reference, finds it through SPKDIAR_HOME
 sys.path.insert(0, os.environ.get('SPKDIAR_HOME') or os.path.dirname(os.path.dirname(os.path.realpath(__file__))))
 import spkdiar  # noqa: E402,F401
-from spkdiar import change_detection
-change_detection.main()
+from spkdiar import glue
+glue.elan_main()

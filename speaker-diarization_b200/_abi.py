@@ -33,7 +33,7 @@ SYMBOLS = (
     'spkdiar_cluster_run_sharded', 'spkdiar_cluster_run_sharded_nccl', 'spkdiar_nccl_unique_id',
     'spkdiar_cluster_run_sharded_p2p', 'spkdiar_mailbox_create', 'spkdiar_mailbox_open',
     'spkdiar_mailbox_close', 'spkdiar_mailbox_free',
-    'spkdiar_cluster_free', 'spkdiar_cluster_matrix',
+    'spkdiar_cluster_free', 'spkdiar_cluster_matrix', 'spkdiar_cluster_rowlog',
     'spkdiar_features_upload_batch', 'spkdiar_cluster_batch', 'spkdiar_selftest_stitch',
     'spkdiar_gw_multi_begin', 'spkdiar_gw_multi_wait', 'spkdiar_gw_multi_where', 'spkdiar_gw_multi_end',
     'spkdiar_ctx_exec',
@@ -121,6 +121,7 @@ def load_library(path=None):
         'spkdiar_mailbox_free': (C.c_int, [vp, vp]),
         'spkdiar_cluster_free': (C.c_int, [vp]),
         'spkdiar_cluster_matrix': (C.c_int, [vp, pdbl, C.POINTER(C.c_uint8)]),
+        'spkdiar_cluster_rowlog': (C.c_int, [vp, pdbl, i64]),
         'spkdiar_features_upload_batch': (C.c_int, [vp, C.POINTER(vp), pi64, i32, i32, C.POINTER(vp), pi64]),
         'spkdiar_cluster_batch': (C.c_int, [vp, i32, pi64, pi64, pi64, C.c_int, dbl, dbl, i32, i32, vp, pi64, pdbl]),
         'spkdiar_selftest_stitch': (C.c_int, [C.c_uint64, dbl, i64, i32]),
@@ -279,10 +280,14 @@ class Features(object):
         self.ctx = ctx
         self.h = handle
         self.n = int(n)
+        ctx.live_features = getattr(ctx, 'live_features', 0) + 1
+        ctx.peak_features = max(getattr(ctx, 'peak_features', 0), ctx.live_features)
 
     def close(self):
-        if getattr(self, 'h', None) and self.ctx.h:
-            self.ctx.lib.spkdiar_features_free(self.h)
+        if getattr(self, 'h', None):
+            if self.ctx.h:
+                self.ctx.lib.spkdiar_features_free(self.h)
+            self.ctx.live_features -= 1
         self.h = None
 
     def __enter__(self):
@@ -342,7 +347,7 @@ class Features(object):
         prm = GwParams(float(rate), float(winsize), float(winstep), float(deltaws), float(threshold),
                        float(lambdac), int(metric), int(max_groups))
         if cap is None:
-            unit = max(float(rate) / 2 - float(rate) / 10, 1.0)
+            unit = max(min(float(rate) / 2 - float(rate) / 10, float(winstep)), 1.0)
             cap = int(sum(2 * ((b - a) / unit + 2) for a, b in zip(seg_a, seg_b))) + 16
         first = np.zeros(nchain + 1, dtype=np.int64)
         while True:
@@ -367,7 +372,7 @@ class Features(object):
                                            int(r['metric']), int(max_groups)) for r in runs])
         caps = np.zeros(nrun, dtype=np.int64)
         for k, r in enumerate(runs):
-            unit = max(float(r['rate']) / 2 - float(r['rate']) / 10, 1.0)
+            unit = max(min(float(r['rate']) / 2 - float(r['rate']) / 10, float(r['winstep'])), 1.0)
             caps[k] = int(sum(2 * ((b - a) / unit + 2) for a, b in zip(seg_a, seg_b))) + 16
         firsts = [np.zeros(nchain + 1, dtype=np.int64) for _ in range(nrun)]
         while True:
@@ -422,7 +427,8 @@ class GwMulti(object):
         """-> (window records, win_first) of search r, as ``Features.gw_run`` returns them."""
         if not 0 <= int(r) < len(self.runs):
             raise SpkdiarError(-2, 'search %d of %d' % (r, len(self.runs)))
-        unit = max(float(self.runs[r]['rate']) / 2 - float(self.runs[r]['rate']) / 10, 1.0)
+        unit = max(min(float(self.runs[r]['rate']) / 2 - float(self.runs[r]['rate']) / 10,
+                       float(self.runs[r]['winstep'])), 1.0)
         cap = int(sum(2 * ((b - a) / unit + 2) for a, b in zip(self.seg_a, self.seg_b))) + 16
         first = np.zeros(self.nchain + 1, dtype=np.int64)
         while True:
@@ -621,6 +627,14 @@ class Clusters(object):
             self.h, float(threshold), int(max_spk), int(rank), int(nranks), arr, int(seq_base),
             out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(nm), _p(stats, C.c_double)))
         return out[:nm.value], stats
+
+    def rowlog(self, cap_rows):
+        """Test hook: the next run() also records row ``a`` of the pair matrix after every merge
+        (original indices); returns the (cap_rows, n) array the run will fill."""
+        self._rowlog = np.zeros((cap_rows, self.n)) if cap_rows > 0 else None
+        self.ctx._check(self.ctx.lib.spkdiar_cluster_rowlog(
+            self.h, _p(self._rowlog, C.c_double) if cap_rows > 0 else None, cap_rows))
+        return self._rowlog
 
     def matrix(self):
         m = np.empty((self.n, self.n))

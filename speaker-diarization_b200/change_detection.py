@@ -97,6 +97,11 @@ class Detector(object):
         self.deltaws = np.floor(self.rate * deltaws)               # CD:508
         self.winsize = np.floor(winsize * self.rate)               # CD:526
         self.winstep = np.floor(winstep * self.rate)               # CD:527
+        if method in ('sw', 'gw') and not self.winstep >= 1:
+            # `start += winstep` (CD:341) / `end += ws` with ws clamped to winstep (CD:273-280) stop advancing:
+            # the reference spins until it is interrupted; a device-resident search cannot be, so this is refused
+            raise ValueError('window step of %r s is below one frame at %r fps: the search would never end'
+                             % (winstep, self.rate))
         self.threshold = threshold
         self.lambdac = lambdac
         self.tt = tt
@@ -433,6 +438,10 @@ class Detector(object):
                 line = recipe[l]
                 if line.audio != this_wav:
                     flush()
+                    # the reference holds one wav at a time (CD:367-369); a handle keeps 6.7 KB of statistics
+                    # per frame on the device, so the previous wav is released before the next is read
+                    while owned:
+                        owned.pop().close()
                     this_wav = line.audio
                     feat = load(line)
                     if loader is None:

@@ -260,7 +260,9 @@ class Clusterer(object):
             for l, line in enumerate(recipe):
                 if line.audio != this_wav:
                     this_wav = line.audio
-                    if feat is not None and loader is None and self.method == 'hi':
+                    # one wav resident at a time, as in the reference (CL1:268-271): every distance of either
+                    # method reads the frames of the wav loaded LAST (Q10), so the previous handle is dead
+                    if feat is not None and loader is None:
                         feat.close()
                         owned.remove(feat)
                     feat = load(line)

@@ -25,6 +25,7 @@ from . import recipe as recipe_mod
 
 D2_CHANGE = dict(method='gw', distance='BIC', winsize=1.0, winstep=3.0, deltaws=0.1, lambdac=1.0)
 D2_CLUSTER = dict(method='hi', distance='BIC', lambdac=1.3)
+BATCH_MAX_SEGMENTS = 512        # larger clustering problems leave the one-CTA-per-recording engine
 
 
 def shard(n_items, rank, world):
@@ -107,8 +108,20 @@ class _BatchJob(object):
 
     def stage_c(self):
         c0 = self.cls[0]
-        self.merged = self.pack.cluster_batch([self.problems[r] for r in self.live], c0.metric, c0.lambdac,
-                                              self.threshold, 0, 1) if self.live else []
+        # The batched engine runs ONE CTA per recording and sizes its workspaces from the largest problem of
+        # the batch (148 x nmax^2 doubles): recordings with many turns go through the resident engine (whole
+        # GPU per recording) so that one long file neither starves nor overflows the batch.
+        small = [r for r in self.live if len(self.problems[r]) <= BATCH_MAX_SEGMENTS]
+        got = self.pack.cluster_batch([self.problems[r] for r in small], c0.metric, c0.lambdac,
+                                      self.threshold, 0, 1) if small else []
+        by_rec = dict(zip(small, got))
+        for r in self.live:
+            if r not in by_rec:
+                sa = [a for a, _ in self.problems[r]]
+                sb = [b for _, b in self.problems[r]]
+                with self.views[r].cluster(sa, sb, c0.metric, c0.lambdac) as cl:
+                    by_rec[r] = cl.run(self.threshold, 0, 1)
+        self.merged = [by_rec[r] for r in self.live]
         return self
 
     def stage_d(self):
@@ -255,6 +268,7 @@ def items_from_recipes(recipe_paths, feapath, feaext='.fea'):
     recording's batch is uploaded."""
     from .feacat import feature_file_name, read_features
     items = []
+    seen = {}
     for path in recipe_paths:
         with open(path, 'r') as f:
             lines = f.readlines()
@@ -269,7 +283,12 @@ def items_from_recipes(recipe_paths, feapath, feaext='.fea'):
         def frames(fea=fea):
             dim, x = read_features(fea)
             return x
-        items.append((op.splitext(op.basename(path))[0], lines, frames))
+        name = op.splitext(op.basename(path))[0]
+        if name in seen:
+            raise ValueError('recipes %s and %s would both write %s.recipe: item names must be unique'
+                             % (seen[name], path, name))
+        seen[name] = path
+        items.append((name, lines, frames))
     return items
 
 

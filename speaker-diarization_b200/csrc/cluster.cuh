@@ -32,6 +32,8 @@ struct spkdiar_clus {
     double* M = nullptr;         // [n][n]
     uint8_t* alive = nullptr;    // [n] (final state, for the test hook)
     bool ran = false;
+    double* rowlog_host = nullptr;   // test hook (spkdiar_cluster_rowlog): row a after every merge
+    int64_t rowlog_cap = 0;
 };
 
 namespace spk {
@@ -182,6 +184,8 @@ struct ClDev {
     long long* nmerge;           // merges performed
     double* final_min;           // the minimum that stopped the loop
     unsigned long long* dbg;     // optional phase cycle counters of CTA 0
+    double* rowlog;              // test hook: [rowlog_cap][n] row a of M as rewritten by merge nm (else null)
+    long long rowlog_cap;
     // host-driven (sharded) run only: state that the persistent kernel keeps on chip
     uint32_t* abits_g;           // [ceil(n/32)] alive mask
     double* pend;                // [REC + 2] merged record, ln|S_ab|, index a (+1; 0 = nothing pending)
@@ -192,7 +196,8 @@ struct ClDev {
     const ClBest* gathered;      // [nranks] candidates of all ranks (all-gather target)
     double* det;                 // [0] max_det [1] min_det
     // peer-memory exchange inside the persistent kernel
-    ClMail* mbox[CL_MAX_RANKS];  // mbox[r]: rank r's mailbox [2][nranks] as mapped on THIS device (mbox[rank]: local)
+    ClMail* mbox[CL_MAX_RANKS];  // mbox[r]: rank r's mailbox [3][nranks] as mapped on THIS device (mbox[rank]: local);
+                                 // sets 0 / 1: candidates of even / odd merges, set 2: the final statistics round
     unsigned long long seq_base; // sequence numbers of this run start above it
     int* err;                    // set when a peer did not answer in time
 };
@@ -551,14 +556,20 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
             for (int q = threadIdx.x; q < REC; q += CL_THREADS) g.rec[a * REC + q] = sm.merged[q];
             if (threadIdx.x == 0) g.ld[a] = ld_ab;
         }
+        if (g.rowlog && nm < g.rowlog_cap)                  // test hook: the rewritten row, for the host's argmin replay
+            for (int64_t cidx = (int64_t)blockIdx.x * CL_THREADS + threadIdx.x; cidx < n; cidx += (int64_t)gridDim.x * CL_THREADS)
+                g.rowlog[nm * n + cidx] = __ldcg(g.M + a * n + cidx);
         --nalive;
         ++nm;
     }
     if (g.nranks > 1 && blockIdx.x == 0 && warp == 0 && !*((volatile int*)g.err)) {
         // one more round: (max, min) over every finite distance any rank computed.  All ranks left the
-        // loop at the same iteration, so the sequence number nm + 2 and the slot parity agree.
+        // loop at the same iteration, so the sequence number nm + 2 agrees.  The round has its OWN slots (the
+        // third set): a rank that has collected it and returns may start the next run and post that run's first
+        // candidate (parity-0 slots) while a slower peer is still reading this round - the two never share a slot,
+        // and nobody can reach the next run's statistics round before every rank has left this run.
         const unsigned long long want = g.seq_base + (unsigned long long)nm + 2ULL;
-        const int slot = (int)((nm + 1) & 1) * g.nranks;
+        const int slot = 2 * g.nranks;
         const unsigned long long kmax = __ldcg(g.stat + 0), kmin = __ldcg(g.stat + 1);
         if (lane < g.nranks) {
             ClMail* dst = g.mbox[lane] + slot + g.rank;

@@ -9,8 +9,11 @@ writes in ``spk-diarization2.py`` (lines 111-112 and 131-132).
 * ``aku2ann.py``: a recipe -> the simple annotation format (``start<TAB>end<TAB>speaker``
   under a ``# audio`` header per file; aku2ann.py:31-38).
 
+* ``aku2elan.py``: a recipe -> an ELAN 2.7 annotation document (aku2elan.py:45-99), written
+  directly as text in the form lxml gives ``tree.write(..., pretty_print=True)`` (lxml is not
+  needed).
+
 Pure host code: no device work, same command lines, same stdout text, Python-2 float text.
-``aku2elan.py`` (ELAN XML through lxml) is not built.
 """
 
 import argparse
@@ -99,9 +102,8 @@ def exp_turns(expfile, rate, ms, mns, sbe=0.0, see=0.0):
     return tr.turns
 
 
-def vad_main(argv=None, stdout=None):
-    """voice-detection2.py:133-198."""
-    out = stdout if stdout is not None else sys.stdout
+def vad_parser():
+    """The command line of voice-detection2.py:133-170."""
     p = argparse.ArgumentParser(description='Creates a recipe from the Speech Activity Detection '
                                 'generate_exp.py output (.exp files), that is, speech/non-speech '
                                 'turn detection')
@@ -117,7 +119,13 @@ def vad_main(argv=None, stdout=None):
                    help='Time removed before each detected segment, default 0.0.')
     p.add_argument('-see', dest='seg_end_exp', type=float, default=0.0,
                    help='Time added after each detected segment, default 0.0.')
-    args = p.parse_args(argv)
+    return p
+
+
+def vad_main(argv=None, stdout=None):
+    """voice-detection2.py:133-198."""
+    out = stdout if stdout is not None else sys.stdout
+    args = vad_parser().parse_args(argv)
 
     def log(*items):
         out.write(p2line(*items) + '\n')
@@ -209,4 +217,122 @@ def ann_main(argv=None, stdout=None):
             outf.write(body.getvalue())
     else:
         log('Writing output to: stdout')
+        out.write(body.getvalue())
+
+
+# ---- aku2elan.py ---------------------------------------------------------------------------------
+
+def iso_now():
+    """aku2elan.py:10-17: local time in ISO format with the UTC offset ELAN expects."""
+    from datetime import datetime, timezone
+    now = datetime.now()
+    delta = now - datetime.now(timezone.utc).replace(tzinfo=None)
+    hh, mm = divmod((delta.days * 24 * 60 * 60 + delta.seconds + 30) // 60, 60)
+    return '%s%+02d:%02d' % (now.isoformat(), hh, mm)
+
+
+def _xml(text, attr=False):
+    """Character escaping of libxml2's ASCII serialisation."""
+    out = []
+    for ch in text:
+        o = ord(ch)
+        if ch == '&':
+            out.append('&amp;')
+        elif ch == '<':
+            out.append('&lt;')
+        elif ch == '>':
+            out.append('&gt;')
+        elif attr and ch == '"':
+            out.append('&quot;')
+        elif (attr and ch in '\n\r\t') or o > 126:
+            out.append('&#%d;' % o)
+        else:
+            out.append(ch)
+    return ''.join(out)
+
+
+def recipe_to_elan(lines, outf, report=None, date=None):
+    """aku2elan.py:20-99.  Lines lacking audio / lna / start / end are reported and skipped; two time
+    slots and one alignable annotation per line (``int(seconds * 1000)`` milliseconds, fp64 product
+    truncated as the reference does); the speaker tag, when present, is the annotation value.  The
+    media descriptor is the first line's audio (an empty recipe raises IndexError, an unknown media
+    type TypeError - as the reference)."""
+    from mimetypes import guess_type
+    rows = []
+    for text in lines:
+        m = [r.search(text) for r in _ANN]
+        if any(x is None for x in m):
+            if report is not None:                      # two print statements (aku2elan.py:41-42)
+                report('Recipe line without recognizable data:')
+                report(text)
+            continue
+        spk = _SPK.search(text)
+        rows.append((m[0].group(1), float(m[2].group(1)), float(m[3].group(1)), spk.group(1) if spk else ''))
+    media = rows[0][0]
+    mime = guess_type(media)[0]
+    if mime is None:
+        raise TypeError("Argument must be bytes or unicode, got 'NoneType'")
+    w = outf.write
+    w('<ANNOTATION_DOCUMENT xmlns:xsi="http://www.w3.org/2001/XMLSchema-instance" AUTHOR="" DATE="%s" '
+      'FORMAT="2.7" VERSION="2.7" xsi:noNamespaceSchemaLocation="http://www.mpi.nl/tools/elan/EAFv2.7.xsd">\n'
+      % _xml(date if date is not None else iso_now(), True))
+    w('  <HEADER MEDIA_FILE="" TIME_UNITS="milliseconds">\n')
+    w('    <MEDIA_DESCRIPTOR MEDIA_URL="%s" MIME_TYPE="%s" RELATIVE_MEDIA_URL=""/>\n'
+      % (_xml('file://' + media, True), _xml(mime, True)))
+    w('    <PROPERTY NAME="lastUsedAnnotationId">%d</PROPERTY>\n' % len(rows))
+    w('  </HEADER>\n')
+    w('  <TIME_ORDER>\n')
+    for k, (_, start, end, _) in enumerate(rows):
+        w('    <TIME_SLOT TIME_SLOT_ID="ts%d" TIME_VALUE="%d"/>\n' % (2 * k + 1, int(start * 1000)))
+        w('    <TIME_SLOT TIME_SLOT_ID="ts%d" TIME_VALUE="%d"/>\n' % (2 * k + 2, int(end * 1000)))
+    w('  </TIME_ORDER>\n')
+    w('  <TIER DEFAULT_LOCALE="en" LINGUISTIC_TYPE_REF="default-lt" TIER_ID="Speakers">\n')
+    for k, (_, _, _, spk) in enumerate(rows):
+        w('    <ANNOTATION>\n')
+        head = '      <ALIGNABLE_ANNOTATION ANNOTATION_ID="a%d" TIME_SLOT_REF1="ts%d" TIME_SLOT_REF2="ts%d"' \
+            % (k + 1, 2 * k + 1, 2 * k + 2)
+        if spk:
+            w(head + '>\n')
+            w('        <ANNOTATION_VALUE>%s</ANNOTATION_VALUE>\n' % _xml(spk))
+            w('      </ALIGNABLE_ANNOTATION>\n')
+        else:
+            w(head + '/>\n')
+        w('    </ANNOTATION>\n')
+    w('  </TIER>\n')
+    w('  <LINGUISTIC_TYPE GRAPHIC_REFERENCES="false" LINGUISTIC_TYPE_ID="default-lt" TIME_ALIGNABLE="true"/>\n')
+    w('  <LOCALE COUNTRY_CODE="US" LANGUAGE_CODE="en"/>\n')
+    w('</ANNOTATION_DOCUMENT>\n')
+
+
+def elan_main(argv=None, stdout=None, date=None):
+    """aku2elan.py:102-128."""
+    out = stdout if stdout is not None else sys.stdout
+    p = argparse.ArgumentParser(description='Converts an AKU recipe to Elan format.')
+    p.add_argument('recfile', type=str, help='Specifies the input recipe file')
+    p.add_argument('-o', dest='outfile', type=str, default=None, help='Specifies an output file, default stdout.')
+    args = p.parse_args(argv)
+
+    def log(*items):
+        out.write(p2line(*items) + '\n')
+
+    log('Reading recipe from:', args.recfile)
+    with open(args.recfile, 'r') as f:
+        lines = f.readlines()
+    import io
+    body = io.StringIO()
+    # the reference parses (and reports bad lines) before it announces the output
+    bad = []
+    try:
+        recipe_to_elan(lines, body, lambda *items: bad.append(items), date)
+    finally:
+        for items in bad:
+            log(*items)
+        if args.outfile is not None:
+            log('Writing output to:', args.outfile)
+        else:
+            log('Writing output to: stdout')
+    if args.outfile is not None:
+        with open(args.outfile, 'w') as outf:
+            outf.write(body.getvalue())
+    else:
         out.write(body.getvalue())

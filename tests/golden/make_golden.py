@@ -125,6 +125,24 @@ def glue_fixtures():
                    ann=open(outp).read())
     json.dump(fix, open(os.path.join(HERE, 'aku2ann.json'), 'w'), indent=1, sort_keys=True)
     print('aku2ann', fix['ann'].count('\n'), 'lines')
+    # aku2elan.py: the reference's own tree building, serialised by oracle/lxml_shim.py (lxml is absent)
+    import re
+    with tempfile.TemporaryDirectory() as tmp:
+        lines = src.splitlines(True)
+        lines.insert(2, 'a line without fields\n')
+        lines.insert(4, 'audio=/syn/other.wav lna=b_1 start-time=1.1 end-time=2.3\n')
+        lines.insert(5, 'audio=/syn/o<&>"ther.wav lna=b_2 start-time=0.57 end-time=4.35 speaker=sp<&"k\n')
+        text = ''.join(lines)
+        rp, outp = os.path.join(tmp, 'in.recipe'), os.path.join(tmp, 'out.eaf')
+        open(rp, 'w').write(text)
+        stdout, _ = ref_exec.run('aku2elan.py', [rp, '-o', outp])
+        to_stdout, _ = ref_exec.run('aku2elan.py', [rp])
+        mask = lambda t: re.sub(r'DATE="[^"]*"', 'DATE="<NOW>"', t).replace(tmp, '<TMP>')      # noqa: E731
+        fix = dict(name='aku2elan', script='aku2elan.py', recipe_in=text, stdout=mask(stdout),
+                   eaf=mask(open(outp).read()), to_stdout=mask(to_stdout),
+                   note='lxml is not installed here: serialisation by oracle/lxml_shim.py (un-pinned)')
+    json.dump(fix, open(os.path.join(HERE, 'aku2elan.json'), 'w'), indent=1, sort_keys=True)
+    print('aku2elan', fix['eaf'].count('\n'), 'lines')
 
 
 if __name__ == '__main__':

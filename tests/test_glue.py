@@ -82,3 +82,58 @@ def test_aku2ann_reproduces_reference(tmp_path):
     out2 = io.StringIO()
     glue.ann_main([rp], stdout=out2)
     assert out2.getvalue().endswith('Writing output to: stdout\n' + fix['ann'])
+
+
+def _mask(text, tmp):
+    import re
+    return re.sub(r'DATE="[^"]*"', 'DATE="<NOW>"', text).replace(tmp, '<TMP>')
+
+
+def test_aku2elan_reproduces_reference(tmp_path):
+    """aku2elan.py:45-99.  The fixture is the reference's own tree building serialised by
+    oracle/lxml_shim.py (lxml is absent here); the product writes the text directly."""
+    fix = load_golden('aku2elan')
+    tmp = str(tmp_path)
+    rp, outp = os.path.join(tmp, 'in.recipe'), os.path.join(tmp, 'out.eaf')
+    open(rp, 'w').write(fix['recipe_in'])
+    out = io.StringIO()
+    glue.elan_main([rp, '-o', outp], stdout=out)
+    assert _mask(open(outp).read(), tmp) == fix['eaf']
+    assert _mask(out.getvalue(), tmp) == fix['stdout']
+    out2 = io.StringIO()
+    glue.elan_main([rp], stdout=out2)
+    assert _mask(out2.getvalue(), tmp) == fix['to_stdout']
+    # the document is well-formed XML with one annotation and two time slots per recipe line
+    import xml.etree.ElementTree as ET
+    doc = ET.parse(outp).getroot()
+    n = len(doc.findall('./TIER/ANNOTATION'))
+    assert n == 24 and len(doc.findall('./TIME_ORDER/TIME_SLOT')) == 2 * n
+    assert doc.find('./HEADER/PROPERTY').text == str(n)
+    assert doc.find('./HEADER/MEDIA_DESCRIPTOR').get('MIME_TYPE') == 'audio/x-wav'
+    vals = [a.findtext('./ALIGNABLE_ANNOTATION/ANNOTATION_VALUE') for a in doc.findall('./TIER/ANNOTATION')]
+    assert 'sp<&"k' in vals and None in vals              # escaped tag round-trips; a line without a speaker tag
+
+
+def test_aku2elan_date_and_errors(tmp_path):
+    import re
+    assert re.match(r'^\d{4}-\d\d-\d\dT\d\d:\d\d:\d\d(\.\d+)?[+-]\d{1,2}:\d\d$', glue.iso_now())   # '%+02d' (aku2elan.py:17)
+    rp = str(tmp_path / 'in.recipe')
+    open(rp, 'w').write('nothing here\n')
+    out = io.StringIO()
+    with pytest.raises(IndexError):                       # recipe[0][0] of an empty recipe (aku2elan.py:60)
+        glue.elan_main([rp], stdout=out)
+    assert out.getvalue().startswith('Reading recipe from:') and 'Recipe line without recognizable data:' in out.getvalue()
+    open(rp, 'w').write('audio=/syn/x.unknownext lna=a_1 start-time=0.0 end-time=1.0\n')
+    with pytest.raises(TypeError):                        # MIME_TYPE None is refused by lxml
+        glue.elan_main([rp], stdout=io.StringIO())
+
+
+@pytest.mark.skipif(not ref_exec.available(), reason='needs /root/reference')
+def test_aku2elan_matches_live_reference(tmp_path):
+    fix = load_golden('aku2elan')
+    tmp = str(tmp_path)
+    rp = os.path.join(tmp, 'in.recipe')
+    open(rp, 'w').write(fix['recipe_in'])
+    want, _ = ref_exec.run('aku2elan.py', [rp, '-o', os.path.join(tmp, 'w.eaf')])
+    assert _mask(open(os.path.join(tmp, 'w.eaf')).read(), tmp) == fix['eaf']
+    assert _mask(want, tmp).replace('w.eaf', 'out.eaf') == fix['stdout']

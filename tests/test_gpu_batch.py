@@ -143,6 +143,24 @@ def test_diarize_batch_equals_one_at_a_time_and_oracle(ctx):
     assert out.getvalue() == batched[1][1]
 
 
+def test_large_problems_of_a_batch_take_the_resident_engine(ctx, monkeypatch):
+    """A recording with more turns than the one-CTA engine should take is clustered by the resident engine
+    inside the same batch; the recipes do not change (the two engines are bit-identical)."""
+    items = []
+    for k in range(4):
+        rec = synth.make_recording(930 + k, 6000 + 2000 * k, 3, turn_lo=3, turn_hi=6)
+        items.append((synth.one_line_recipe('/syn/r%d.wav' % k, rec), rec.frames))
+    want = corpus.diarize_batch(ctx, items, 100)
+    sizes = sorted(r[2]['turns'] for r in want)
+    monkeypatch.setattr(corpus, 'BATCH_MAX_SEGMENTS', sizes[1])        # the two largest leave the batch
+    l0 = ctx.launches
+    got = corpus.diarize_batch(ctx, items, 100)
+    assert got == want
+    monkeypatch.setattr(corpus, 'BATCH_MAX_SEGMENTS', 0)               # all of them
+    assert corpus.diarize_batch(ctx, items, 100) == want
+    assert ctx.launches > l0
+
+
 def test_overlapped_batches_equal_batches(ctx):
     """The pipelined driver (device stages on a worker thread, host replay on this one) returns
     exactly what the synchronous one returns, batch by batch."""

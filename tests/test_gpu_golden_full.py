@@ -1,0 +1,291 @@
+"""GPU parity against the FULL-SIZE golden fixtures (tests/golden/full/, made by
+tests/golden/make_golden_full.py from the reference's own scripts and the oracle's trace):
+
+* BASELINE config 2, the WHOLE hour, growing window with BIC, GLR (-t 1500) and KL2 (-t 4000):
+  every window record (start, end, best offset, decision, fine-tuned offset) bit-identical,
+  distances to 1e-9, the recipe byte-identical, the log to 1e-9;
+* config 3 cut to 200 / 400 segments, spk-clustering.py and spk-clustering2.py: the merge
+  sequence identical, distances to 1e-9, recipe byte-identical;
+* three ten-minute files of config 4 through both stages (one at a time and as a device batch);
+* config 3 at FULL size (1,978 segments): the agglomeration replayed on the host from the rows the
+  device wrote - every merge must be ``ndarray.argmin`` of the live matrix at that moment.
+
+Distances are compared as everywhere else: |d_gpu - d_ref| <= 1e-9 * max(|d_ref|, largest
+0.5 N ln|S| term the distance is a difference of).  Every test also writes a MARGIN AUDIT
+(gpurun_out/audit_*.json; copied to profiles/): the observed errors and how far the reference's own
+decisions (maxd vs threshold, winner vs runner-up) are from flipping, in units of that tolerance."""
+
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+import spkdiar                              # noqa: F401
+from conftest import GOLDEN_DIR, logs_match, run_product
+from spkdiar import _abi, synth
+
+pytestmark = pytest.mark.gpu
+
+FULL = os.path.join(GOLDEN_DIR, 'full')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+AUDIT_DIR = os.environ.get('SPKDIAR_AUDIT_DIR', os.path.join(ROOT, 'gpurun_out'))
+REL = 1e-9
+
+
+def load_full(name):
+    p = os.path.join(FULL, name + '.json')
+    if not os.path.isfile(p):
+        pytest.skip('fixture %s not generated' % name)
+    with open(p) as f:
+        return json.load(f)
+
+
+def write_audit(name, doc):
+    try:
+        os.makedirs(AUDIT_DIR, exist_ok=True)
+        with open(os.path.join(AUDIT_DIR, 'audit_%s.json' % name), 'w') as f:
+            json.dump(doc, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    c = _abi.Context(0)
+    yield c
+    c.close()
+
+
+def _half_n_logdet(x):
+    """0.5 N ln|S| of a frame slice, the size of the terms a BIC / GLR distance is a difference of."""
+    if x.shape[0] < 2:
+        return 0.0
+    sign, ld = np.linalg.slogdet(np.cov(x, rowvar=0))
+    return 0.5 * x.shape[0] * abs(ld) if np.isfinite(ld) else 0.0
+
+
+def _sha(frames):
+    import hashlib
+    return hashlib.sha256(frames.tobytes()).hexdigest()
+
+
+# ---------------------------------------------------------------- config 2: the whole hour ----------
+
+@pytest.fixture(scope='module')
+def hour(ctx):
+    rec = synth.config2()
+    feat = ctx.upload(rec.frames)
+    yield rec, feat
+    feat.close()
+
+
+@pytest.mark.parametrize('name,metric,thr', [('c2_bic', _abi.BIC, 0.0), ('c2_glr', _abi.GLR, 1500.0),
+                                             ('c2_kl2', _abi.KL2, 4000.0)])
+def test_config2_whole_hour_records_equal_reference(hour, name, metric, thr):
+    gold = load_full(name)
+    rec, feat = hour
+    n = rec.frames.shape[0]
+    assert n == gold['frames'] == 360000 and _sha(rec.frames) == gold['frames_sha256']
+    win, _ = feat.gw_run([0], [n], 100.0, 100.0, 300.0, 10.0, thr, 1.0, metric)
+    g = gold['windows']
+    assert len(win) == len(g['start']), (len(win), len(g['start']))
+    x = rec.frames
+    errs, units, refs, thr_margin, gap_margin = [], [], [], [], []
+    for k, r in enumerate(win):
+        want_pos = bool(g['positive'][k])
+        assert r['start'] == g['start'][k] and r['end'] == g['end'][k], (k, r, g['start'][k], g['end'][k])
+        assert bool(r['positive']) == want_pos, (k, r)
+        assert g['maxi'][k] is not None and r['maxi'] == g['maxi'][k], (k, r, g['maxi'][k])
+        s, e = int(r['start']), int(r['end'])
+        m = int(r['start'] + r['maxi'])
+        if metric == _abi.KL2:
+            # the reference's KL2 inverts the covariance of each side: conditioning-limited below 2 d frames
+            rel = REL if min(m - s, e - m) >= 78 else 1e-6
+            unit = rel * abs(g['maxd'][k])
+        else:
+            scale = max(_half_n_logdet(x[s:m]), _half_n_logdet(x[m:e]), _half_n_logdet(x[s:e]))
+            unit = REL * max(abs(g['maxd'][k]), scale)
+        pairs = [(r['maxd'], g['maxd'][k], g['gap'][k])]
+        if want_pos:
+            assert r['maxi_fine'] == g['maxi_fine'][k], (k, r, g['maxi_fine'][k])
+            pairs.append((r['maxd_fine'], g['maxd_fine'][k], g['gap_fine'][k]))
+        for got, ref, gap in pairs:
+            err = abs(got - ref)
+            assert err <= unit, (k, got, ref, err / unit)
+            errs.append(err)
+            units.append(unit)
+            refs.append(abs(ref))
+            thr_margin.append(abs(ref - thr))
+            gap_margin.append(gap)
+    errs, units, refs = np.array(errs), np.array(units), np.array(refs)
+    thr_margin, gap_margin = np.array(thr_margin), np.array(gap_margin)
+    write_audit(name, dict(
+        windows=len(win), changes=int(np.sum(win['positive'])),
+        tolerance='1e-9 * max(|d|, largest 0.5 N ln|S| term)' if metric != _abi.KL2
+        else '1e-9 * |d| (1e-6 * |d| when a side has fewer than 78 frames)',
+        err_over_tolerance_max=float(np.max(errs / units)), err_over_tolerance_median=float(np.median(errs / units)),
+        err_abs_max=float(errs.max()), err_rel_to_d_max=float(np.max(errs / np.maximum(refs, 1e-300))),
+        err_rel_to_d_median=float(np.median(errs / np.maximum(refs, 1e-300))),
+        threshold_margin_min_abs=float(thr_margin.min()),
+        threshold_margin_min_in_tolerances=float(np.min(thr_margin / units)),
+        runner_up_gap_min_abs=float(gap_margin.min()),
+        runner_up_gap_min_in_tolerances=float(np.min(gap_margin / units)),
+        decisions_inside_tolerance=int(np.sum(thr_margin <= units) + np.sum(gap_margin <= units)),
+        decisions_inside_observed_error=int(np.sum(thr_margin <= errs) + np.sum(gap_margin <= errs))))
+    # positions bit-identical above; no decision of the reference lies inside the error the device made
+    assert np.all(thr_margin > errs)
+
+
+@pytest.mark.parametrize('name', ['c2_bic', 'c2_glr', 'c2_kl2'])
+def test_config2_whole_hour_cli_equals_reference(name, tmp_path, ctx):
+    gold = load_full(name)
+    rec = synth.config2()
+    rpath, feadir = synth.write_case(str(tmp_path), 'c2', rec, synth.one_line_recipe('/syn/c2.wav', rec))
+    out = str(tmp_path / 'out.recipe')
+    stdout, _ = run_product('cd', 0, [rpath, feadir, '-o', out] + gold['flags'], ctx)
+    assert open(out).read() == gold['recipe']
+    bad = logs_match(stdout.replace(str(tmp_path), '<TMP>'), gold['stdout'], 1e-6 if name == 'c2_kl2' else REL)
+    assert bad is None, bad
+
+
+# ---------------------------------------------------------------- config 3 cut to 200 / 400 ----------
+
+def _c3_cut(nseg):
+    full = synth.config3()
+    cut = full.turns[nseg - 1][1]
+    return synth.Recording(full.frames[:cut].copy(), full.turns[:nseg], full.rate)
+
+
+@pytest.mark.parametrize('name', ['c3_cl1_200', 'c3_cl2_200', 'c3_cl1_400', 'c3_cl2_400'])
+def test_config3_cut_merge_sequence_equals_reference(name, tmp_path, ctx):
+    gold = load_full(name)
+    variant = gold['variant']
+    nseg = int(name.rsplit('_', 1)[1])
+    rec = _c3_cut(nseg)
+    assert _sha(rec.frames) == gold['frames_sha256']
+    sa, sb = [t[0] for t in rec.turns], [t[1] for t in rec.turns]
+    with ctx.upload(rec.frames) as feat, feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
+        merges, stats = cl.run(0.0, 0, variant)
+    want = gold['merges']
+    assert len(merges) == len(want)
+    members = [[k] for k in range(nseg)]
+    ratios, gaps = [], []
+    for m, w in zip(merges, want):
+        a, b = int(m['a']), int(m['b'])
+        assert (a, b) == (w[0], w[1]), (m, w)
+        fa = np.concatenate([rec.frames[sa[k]:sb[k]] for k in members[a]])
+        fb = np.concatenate([rec.frames[sa[k]:sb[k]] for k in members[b]])
+        scale = max(_half_n_logdet(fa), _half_n_logdet(fb), _half_n_logdet(np.concatenate((fa, fb))))
+        unit = REL * max(abs(w[2]), scale)
+        err = abs(m['d'] - w[2])
+        if variant == 1 or np.isfinite(w[2]):
+            assert err <= unit, (m, w, err / unit)
+            ratios.append(err / unit)
+            gaps.append(w[3] / unit)
+        members[a].extend(members[b])
+        members.pop(b)
+    write_audit(name, dict(segments=nseg, merges=len(merges), err_over_tolerance_max=float(max(ratios)),
+                           runner_up_gap_min_in_tolerances=float(min(gaps)),
+                           merges_with_gap_inside_tolerance=int(sum(1 for v in gaps if v <= 1.0))))
+    # and through the command line: recipe byte for byte, log numbers to 1e-9
+    rpath, feadir = synth.write_case(str(tmp_path), 'c3', rec, synth.turn_recipe('/syn/c3.wav', rec))
+    assert open(rpath).read() == gold['recipe_in']
+    out = str(tmp_path / 'out.recipe')
+    stdout, _ = run_product('cl', variant, [rpath, feadir + '/', '-o', out] + gold['flags'], ctx)
+    assert open(out).read() == gold['recipe']
+    bad = logs_match(stdout.replace(str(tmp_path), '<TMP>'), gold['stdout'], REL)
+    assert bad is None, bad
+
+
+# ---------------------------------------------------------------- config 4: both stages ----------
+
+@pytest.mark.parametrize('index', [0, 1, 2])
+def test_config4_file_both_stages_equal_reference(index, tmp_path, ctx):
+    gold = load_full('c4_f%d' % index)
+    rec = synth.config4_file(index)
+    assert _sha(rec.frames) == gold['frames_sha256']
+    wav = 'c4_%d' % index
+    rpath, feadir = synth.write_case(str(tmp_path), wav, rec, synth.one_line_recipe('/syn/%s.wav' % wav, rec))
+    mid, out = str(tmp_path / 'turns.recipe'), str(tmp_path / 'out.recipe')
+    s1, _ = run_product('cd', 0, [rpath, feadir, '-o', mid] + gold['flags_cd'], ctx)
+    assert open(mid).read() == gold['recipe_cd']
+    assert logs_match(s1.replace(str(tmp_path), '<TMP>'), gold['stdout_cd'], REL) is None
+    s2, _ = run_product('cl', 1, [mid, feadir + '/', '-o', out] + gold['flags_cl'], ctx)
+    assert open(out).read() == gold['recipe']
+    bad = logs_match(s2.replace(str(tmp_path), '<TMP>'), gold['stdout_cl'], REL)
+    assert bad is None, bad
+
+
+def test_config4_files_as_device_batch_equal_reference(ctx):
+    from spkdiar import corpus
+    golds = [load_full('c4_f%d' % k) for k in range(3)]
+    batch = []
+    for k in range(3):
+        rec = synth.config4_file(k)
+        batch.append((synth.one_line_recipe('/syn/c4_%d.wav' % k, rec), rec.frames))
+    res = corpus.diarize_batch(ctx, batch, frame_rate=100)
+    for (turns, clustered, _), g in zip(res, golds):
+        assert turns == g['recipe_cd']
+        assert clustered == g['recipe']
+
+
+# ---------------------------------------------------------------- config 3 full size: argmin replay ----------
+
+@pytest.mark.parametrize('variant', [1, 2])
+def test_config3_full_size_every_merge_is_argmin_of_live_matrix(variant, ctx):
+    """spk-clustering.py:203-205 / spk-clustering2.py:187-191 at N = 1,978: replay the agglomeration on the
+    host.  The device supplies the initial matrix and, per merge, the row it rewrote; the host keeps the
+    live matrix (dead rows / columns +inf: deleting them preserves the flat order) and requires every merge
+    of the device to be numpy's argmin of it, with the very same double."""
+    rec = synth.config3()
+    sa, sb = [t[0] for t in rec.turns], [t[1] for t in rec.turns]
+    n = len(sa)
+    with ctx.upload(rec.frames) as feat, feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
+        none, _ = cl.run(-np.inf, 0, variant)              # no merge: the initial fill
+        assert len(none) == 0
+        M, alive = cl.matrix()
+        assert alive.all()
+        rows = cl.rowlog(n)
+        merges, stats = cl.run(0.0, 0, variant)
+        Mend, alive_end = cl.matrix()
+    assert len(merges) > 1900
+    live = list(range(n))                                   # compacted index -> original index
+    dead = np.zeros(n, dtype=bool)
+    gaps = []
+    for k, m in enumerate(merges):
+        idx = int(np.argmin(M))                             # NaN first, first flat index wins
+        r, c = divmod(idx, n)
+        a, b = (r, c) if r < c else (c, r)
+        assert (live.index(a), live.index(b)) == (int(m['a']), int(m['b'])), (k, m, a, b)
+        assert M[r, c] == m['d'] or (np.isnan(M[r, c]) and np.isnan(m['d'])), (k, M[r, c], m['d'])
+        if k % 16 == 0:
+            flat = M.ravel().copy()
+            flat[idx] = np.inf
+            if variant == 1:
+                flat[c * n + r] = np.inf
+            gaps.append(float(np.min(flat) - m['d']))
+        # the merge: b dies, row a (and column a in variant 1) as the device rewrote it
+        dead[b] = True
+        live.remove(b)
+        M[b, :] = np.inf
+        M[:, b] = np.inf
+        new = rows[k].copy()
+        keep = M[a, a]
+        new[dead] = np.inf
+        M[a, :] = new
+        M[a, a] = keep
+        if variant == 1:
+            M[:, a] = new
+            M[a, a] = keep
+    # the loop stopped rightly: nothing at or below the threshold is left
+    assert not (np.min(M) <= 0.0)
+    # and the host's live matrix is the device's final matrix
+    al = ~dead
+    assert np.array_equal(al, alive_end)
+    assert np.array_equal(M[np.ix_(al, al)], Mend[np.ix_(al, al)])
+    write_audit('c3_full_argmin_replay_v%d' % variant,
+                dict(segments=n, merges=len(merges), every_merge_is_numpy_argmin=True,
+                     runner_up_gap_min_abs_sampled=float(min(gaps)), merge_distance_min=float(merges['d'].min()),
+                     merge_distance_max=float(merges['d'].max())))

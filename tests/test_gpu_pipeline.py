@@ -236,3 +236,68 @@ def test_corpus_driver_equals_per_file_scripts(tmp_path, ctx):
         assert open(seg).read() == open(str(tmp_path / 'out' / ('r%d.spkc.recipe' % k))).read()
         assert open(clu).read() == open(str(tmp_path / 'out' / ('r%d.recipe' % k))).read()
         assert summ['r%d' % k]['speakers'] >= 1
+
+
+@pytest.mark.parametrize('kind,flags', [('cd', ['-m', 'gw', '-d', 'BIC', '-w', '1.0', '-st', '3.0', '-dws', '0.1', '-l', '1.0']),
+                                        ('cd', ['-m', 'sw', '-d', 'GLR', '-t', '1500', '-w', '2.0']),
+                                        ('cl', ['-m', 'in', '-l', '1.3']), ('cl', ['-m', 'hi', '-l', '1.3'])])
+def test_multi_wav_recipe_keeps_one_wav_resident(kind, flags, tmp_path, ctx):
+    """The reference holds the features of ONE wav at a time (CD:367-369, CL1:268-271); a device handle carries
+    6.7 KB of statistics per frame, so a batch recipe over many wavs must not accumulate them."""
+    lines = []
+    feadir = str(tmp_path / 'fea')
+    os.makedirs(feadir)
+    from spkdiar.feacat import write_features
+    for k in range(4):
+        rec = synth.make_recording(900 + k, 3000, 2, turn_lo=3, turn_hi=6)
+        write_features(os.path.join(feadir, 'w%d.fea' % k), rec.frames)
+        letter = chr(ord('a') + k)
+        lines += synth.turn_recipe('/syn/w%d.wav' % k, rec, letter) if kind == 'cl' else \
+            synth.one_line_recipe('/syn/w%d.wav' % k, rec, letter + '_1')
+    rpath = str(tmp_path / 'multi.recipe')
+    open(rpath, 'w').writelines(lines)
+    live0 = getattr(ctx, 'live_features', 0)
+    ctx.peak_features = live0
+    og, pg = str(tmp_path / 'o.recipe'), str(tmp_path / 'p.recipe')
+    fp = feadir + '/'
+    run_product(kind, 1, [rpath, fp, '-f', '100', '-o', pg] + flags, ctx)
+    assert ctx.peak_features - live0 == 1 and ctx.live_features == live0
+    run_oracle(kind, 1, [rpath, fp, '-f', '100', '-o', og] + flags)
+    assert open(pg).read() == open(og).read()
+
+
+def test_segment_with_fewer_frames_than_dimensions(ctx):
+    """A segment of n <= 39 frames has a covariance of rank < 39: the reference's
+    ``np.log(det(np.cov(.)))`` is then ROUNDING NOISE of LAPACK's LU (measured here: NaN for a
+    negative determinant, a finite value around -100 ... -700 for a positive one, -inf when it
+    underflows; n = 40 is the first well-defined size), so no parity is defined for such entries
+    (rulings).  What must hold: the run completes, every entry that does not involve the short
+    segment is bit-identical to a run without it, and the batch path completes as well."""
+    rec = synth.make_recording(515, 9000, 3, turn_lo=3, turn_hi=6)
+    sa, sb = [t[0] for t in rec.turns], [t[1] for t in rec.turns]
+    short = 4
+    sb2 = list(sb)
+    sb2[short] = sa[short] + 30                                  # 30 frames in 39 dimensions
+    with ctx.upload(rec.frames) as feat:
+        with feat.cluster(sa, sb2, _abi.BIC, 1.3) as cl:
+            cl.run(-np.inf, 0, 1)
+            M, _ = cl.matrix()
+        keep = [k for k in range(len(sa)) if k != short]
+        with feat.cluster([sa[k] for k in keep], [sb[k] for k in keep], _abi.BIC, 1.3) as cl:
+            cl.run(-np.inf, 0, 1)
+            M0, _ = cl.matrix()
+        assert np.array_equal(M[np.ix_(keep, keep)], M0)
+        assert np.all(np.isfinite(M0[~np.eye(len(keep), dtype=bool)]))
+        # a full run terminates (with NaN entries the NaN-first argmin ends the agglomeration at once,
+        # exactly as `distances.min()` does in spk-clustering.py:203-208; otherwise it merges as usual)
+        with feat.cluster(sa, sb2, _abi.BIC, 1.3) as cl:
+            merges, _ = cl.run(0.0, 0, 1)
+        row = np.delete(M[short], short)
+        assert len(merges) == 0 if np.isnan(row).any() else len(merges) >= 0
+    # the corpus batch: a VAD turn shorter than 40 frames next to normal ones
+    lines = ['audio=/syn/s.wav lna=a_1 start-time=0.0 end-time=40.0\n',
+             'audio=/syn/s.wav lna=a_2 start-time=40.5 end-time=40.8\n',
+             'audio=/syn/s.wav lna=a_3 start-time=41.0 end-time=90.0\n']
+    from spkdiar import corpus
+    (seg, clu, summary), = corpus.diarize_batch(ctx, [(lines, rec.frames)], 100)
+    assert seg.count('\n') == clu.count('\n') >= 3 and 'start-time=40.5 end-time=40.8' in seg

@@ -11,9 +11,9 @@ import numpy as np
 import pytest
 
 import spkdiar
-from spkdiar import _abi, feacat, py2fmt, recipe, synth
+from spkdiar import _abi, feacat, glue, py2fmt, recipe, synth
 from spkdiar import change_detection as pcd, clustering as pcl
-from oracle import change_detection as ocd, clustering as ocl, py2compat
+from oracle import change_detection as ocd, clustering as ocl, py2compat, ref_exec
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -117,6 +117,16 @@ def _flags(parser):
     return out
 
 
+def _flags_full(parser):
+    out = {}
+    for a in parser._actions:
+        for s in a.option_strings or [a.dest]:
+            if s in ('-h', '--help'):
+                continue
+            out[s] = (a.default, tuple(a.choices) if a.choices else None, a.type, a.nargs, type(a).__name__, a.dest)
+    return out
+
+
 def test_cli_contract_change_detection():
     """Same flags and defaults as spk-change-detection.py:399-465 (checked
     against the oracle's parser, which is checked against the reference)."""
@@ -138,6 +148,41 @@ def test_cli_contract_clustering(variant):
     assert got['-o'][0] == (None if variant == 1 else 'stdout')
     assert got['-seg'][0] == ('' if variant == 1 else None)
     assert set(got) - set(ref) <= {'--device'}
+
+
+ADDED_FLAGS = {'--device', '--sw-bic', '--bic-cache'}
+
+
+@pytest.mark.skipif(not ref_exec.available(), reason='needs /root/reference')
+@pytest.mark.parametrize('script,build', [
+    ('spk-change-detection.py', lambda: pcd.build_parser()),
+    ('spk-clustering.py', lambda: pcl.build_parser(1)),
+    ('spk-clustering2.py', lambda: pcl.build_parser(2)),
+    ('voice-detection2.py', lambda: glue.vad_parser()),
+])
+def test_cli_tables_equal_the_reference_scripts_own_parsers(script, build):
+    """Flag for flag against the parser the REFERENCE script builds (executed up to its parse_args by
+    oracle/ref_exec.py): option strings, defaults, choices, value types, arity, destinations."""
+    import sys as _sys
+    ref = _flags_full(ref_exec.parser_of(script))
+    got = _flags_full(build())
+    for k, v in ref.items():
+        assert k in got, (script, k)
+        d, choices, typ, nargs, kind, dest = got[k]
+        if v[0] is _sys.stdout or (hasattr(v[0], 'write') and not isinstance(v[0], str)):
+            # `-o` default is the sys.stdout OBJECT in spk-clustering.py (Q14): ours is None, tested as "is None"
+            assert d is None, (script, k)
+        else:
+            assert d == v[0], (script, k, d, v[0])
+        assert (choices, typ, nargs, kind, dest) == v[1:], (script, k, got[k], v)
+    assert set(got) - set(ref) <= ADDED_FLAGS, set(got) - set(ref)
+    oref = {'spk-change-detection.py': lambda: ocd.build_parser(), 'spk-clustering.py': lambda: ocl.build_parser(1),
+            'spk-clustering2.py': lambda: ocl.build_parser(2)}.get(script)
+    if oref:                                                  # the oracle's tables too
+        o = _flags_full(oref())
+        for k, v in ref.items():
+            if not hasattr(v[0], 'write'):
+                assert o[k][0] == v[0] and o[k][1:] == v[1:], (script, k)
 
 
 def test_bic_from_terms_matches_reference_expression():

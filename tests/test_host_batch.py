@@ -127,3 +127,9 @@ def test_items_from_recipes_reads_lazily(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         corpus.items_from_recipes([str(tmp_path / 'bad.recipe')], str(fea))
+    # two recipes with the same basename would silently overwrite each other's output files
+    sub = tmp_path / 'other'
+    sub.mkdir()
+    (sub / 'r0.recipe').write_text(open(paths[0]).read())
+    with pytest.raises(ValueError, match='unique'):
+        corpus.items_from_recipes([paths[0], str(sub / 'r0.recipe')], str(fea))
