@@ -218,9 +218,11 @@ def e2e_step(ctx, host_frames, recipe_lines):
     return texts
 
 
-def cpu_oracle_sample(seconds, rank=0, parallel=False):
+def cpu_oracle_sample(seconds, rank=0, parallel=False, replicas=1):
     """The reference's CPU path (oracle) on the first `seconds` of the recording:
-    the same four passes.  -> (audio_seconds, cpu_wall_seconds, cores)."""
+    the same four passes.  ``parallel``: the three searches of a recording as three processes;
+    ``replicas``: that many recordings side by side (the N-GPU line diarizes N recordings at a time, so the
+    reference arm at N runs 3 N processes).  -> (audio_seconds of all replicas, cpu_wall_seconds, processes)."""
     import warnings
     warnings.simplefilter('ignore')
     rec = make_recording(rank)
@@ -230,14 +232,15 @@ def cpu_oracle_sample(seconds, rank=0, parallel=False):
     t0 = time.perf_counter()
     if parallel:
         import multiprocessing as mp
-        with mp.get_context('fork').Pool(len(jobs)) as pool:
-            pool.starmap(_cpu_job, [(x, j) for j in jobs])
-        cores = len(jobs)
+        nproc = len(jobs) * replicas
+        with mp.get_context('fork').Pool(nproc) as pool:
+            pool.starmap(_cpu_job, [(x, j) for _ in range(replicas) for j in jobs])
+        cores = nproc
     else:
         for j in jobs:
             _cpu_job(x, j)
         cores = 1
-    return n / float(RATE), time.perf_counter() - t0, cores
+    return replicas * n / float(RATE), time.perf_counter() - t0, cores
 
 
 def _cpu_job(x, job):
@@ -256,24 +259,33 @@ def _cpu_job(x, job):
 
 
 def run_reference(args):
+    """The reference arm.  Like for like with our line at N GPUs (N recordings diarized at a time): N replicas of
+    the bounded sample, each as three processes (the reference is single-process Python; its three searches are
+    independent scripts), i.e. 3 N host processes - capped by the host's cores."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+    ncpu = os.cpu_count() or 1
+    replicas = max(1, min(args.gpus, ncpu // 3))
     vals = []
     for k in range(args.warmup + args.steps):
-        audio_s, wall, cores = cpu_oracle_sample(args.cpu_seconds, 0, parallel=True)
+        audio_s, wall, cores = cpu_oracle_sample(args.cpu_seconds, 0, parallel=True, replicas=replicas)
         if k >= args.warmup:
             vals.append((audio_s / 3600.0) / wall)
     v = sum(vals) / len(vals)
-    sample = ('first %d s of the 1-hour recording: oracle gw BIC -> CL1 clustering, gw GLR, gw KL2 as 3 '
-              'parallel processes (the reference is single-process Python; BLAS threads default)' % args.cpu_seconds)
+    sample = ('first %d s of the 1-hour recording: oracle gw BIC -> CL1 clustering, gw GLR, gw KL2 as 3 parallel '
+              'processes per recording x %d recordings side by side = %d processes on %d host cores (the reference is '
+              'single-process Python; 1 BLAS thread each).  same_config holds for the LABEL: the sample is the first '
+              '%d s, which favours the reference (its clustering grows like N^2.7 with the number of turns)'
+              % (args.cpu_seconds, replicas, 3 * replicas, ncpu, args.cpu_seconds))
     print(json.dumps({
         'impl': 'reference', 'metric': 'audio_hours_per_sec_diarized', 'value': v, 'unit': 'audio-hours/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * (args.cpu_seconds / 3600.0) / v, 'higher_is_better': True, 'scaling': 'weak',
+        'ms_per_step': 1e3 * (replicas * args.cpu_seconds / 3600.0) / v, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': workload_config(),
-        'cpu_baseline': {'value': v, 'unit': 'audio-hours/s', 'cores': 3, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': 'audio-hours/s', 'cores': 3 * replicas, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'audio-hours/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
 
@@ -434,6 +446,80 @@ def run_other_workload(args):
         dist.destroy_process_group()
 
 
+C4_FILES = 296                  # the FIXED corpus of the config4 sub-record: recordings 0..295 of synth.config4_file
+C4_BATCH = 74
+C5_SEGMENTS = 23940             # the FIXED long recording of the config5 sub-record (BASELINE config 5 scaled by 1/2)
+
+
+def sub_config4(ctx, rank, world, timed, steps=2):
+    """BASELINE config 4 as it shards: a FIXED corpus of ten-minute recordings, dealt to the ranks by file index
+    (recording k -> rank k % N, spk-diarization2.py:122-128 once per file, no communication), through the drop-in
+    corpus driver with HOST buffers: pinned frames in, recipe text out, device batches overlapped with the host
+    replay.  Strong scaling: the corpus does not grow with N."""
+    import torch
+    from spkdiar import corpus, synth
+    mine = corpus.shard(C4_FILES, rank, world)
+    items = []
+    for k in mine:
+        r = synth.config4_file(k)
+        items.append((synth.one_line_recipe('/syn/c4_%d.wav' % k, r), torch.from_numpy(r.frames).pin_memory()))
+    parts = [[(lines, (t.data_ptr(), t.shape[0])) for lines, t in items[b0:b0 + C4_BATCH]]
+             for b0 in range(0, len(items), C4_BATCH)]
+
+    def step():
+        out = None
+        for got in corpus.diarize_batches(ctx, parts, RATE):
+            out = got
+        return out
+    step()
+    ms, last = timed(step, steps)
+    hours = C4_FILES * (60000 / RATE / 3600.0)
+    return {'what': 'FIXED corpus of %d ten-minute recordings, recording k on rank k %% N, gw BIC change detection + CL1 '
+                    'clustering (spk-diarization2.py flags) through corpus.diarize_batches: pinned host frames in, recipe '
+                    'text out, device batches of <= %d recordings overlapped with the host replay' % (C4_FILES, C4_BATCH),
+            'scaling': 'strong', 'recordings': C4_FILES, 'recordings_this_rank': len(mine), 'steps': steps,
+            'ms_per_step': ms / steps, 'value': steps * hours / (ms / 1e3), 'unit': 'audio-hours/s',
+            'h2d_bytes_per_step': C4_FILES * 60000 * 39 * 4,
+            'last_recording': last[-1][2] if last else None}
+
+
+def sub_config5(ctx, rank, world, timed, dist, steps=2):
+    """BASELINE config 5 as it shards: ONE fixed long recording (%d segments), pair (r, c) of the matrix on rank
+    (r + c) %% N, one persistent kernel per GPU, 16-byte candidates through peer-memory mailboxes per merge
+    (spk-clustering.py:201-237).  Strong scaling.  The merge sequence is hashed so that the lines of different N
+    can be compared.""" % C5_SEGMENTS
+    import hashlib
+    from spkdiar import _abi, sharded, synth
+    rec = synth.config5(n_frames=C5_SEGMENTS * 173)
+    sa, sb = [t[0] for t in rec.turns], [t[1] for t in rec.turns]
+    feat = ctx.upload(rec.frames)
+    mbx = sharded.Mailboxes(ctx) if world > 1 else None
+    box = {}
+
+    def step():
+        with feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
+            if world > 1:
+                m = cl.run_sharded_p2p(0.0, 0, rank, world, mbx.ptrs, mbx.next_base(len(sa)))[0]
+            else:
+                m = cl.run(0.0, 0, 1)[0]
+            box['counters'] = cl.counters()
+        return m
+    try:
+        step()
+        ms, merges = timed(step, steps)
+    finally:
+        if mbx is not None:
+            mbx.close()
+        feat.close()
+    hours = rec.frames.shape[0] / RATE / 3600.0
+    return {'what': 'ONE fixed %.1f-hour recording, %d segments, CL1 -m hi -l 1.3; pair matrix dealt over N GPUs, one '
+                    'persistent kernel per GPU, candidates exchanged through peer-memory mailboxes' % (hours, len(sa)),
+            'scaling': 'strong', 'segments': len(sa), 'steps': steps, 'ms_per_run': ms / steps,
+            'value': steps * hours / (ms / 1e3), 'unit': 'audio-hours/s', 'merges': int(len(merges)),
+            'merge_sequence_sha256': hashlib.sha256(merges.tobytes()).hexdigest()[:16],
+            'cycles_per_merge_cta0': box.get('counters')}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -449,6 +535,8 @@ def main():
     ap.add_argument('--batch', type=int, default=74, help='config4: recordings per device batch (0: one at a time)')
     ap.add_argument('--no-overlap', dest='overlap', action='store_false',
                     help='config4 with --batch: do not overlap device stages and host replay')
+    ap.add_argument('--no-sharded', action='store_true',
+                    help='skip the config4 / config5 sub-records (the two configurations that shard over the GPUs)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -570,8 +658,14 @@ def main():
         rl_all[k] = {'bound': spec['bound'], 'achieved': ach, 'peak': spec['peak'], 'unit': spec['unit'],
                      'frac': ach / spec['peak'], 'peak_source': spec['peak_source'],
                      'ms_per_step': ms_k / steps, 'launches_per_step': n_k / steps, 'traffic': None}
+        if spec['bound'] == 'fp64':         # beside the measured DFMA peak: the nominal one (148 SM x 64 DFMA/clk x 1.965 GHz)
+            rl_all[k]['peak_nominal'] = 37.2
+            rl_all[k]['frac_of_nominal'] = ach / 37.2
     try:                                    # DRAM traffic per launch from this round's ncu captures
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+        tpath = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
+        if not os.path.isfile(tpath):
+            tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+        traffic = json.load(open(tpath))
         for k in rl_all:
             if k in traffic:
                 rl_all[k]['traffic'] = traffic[k]['bytes_per_launch']
@@ -579,6 +673,14 @@ def main():
         pass
     dominant = max(rl_all, key=lambda k: rl_all[k]['ms_per_step'])
     roofline = dict(rl_all[dominant], kernel=dominant)
+
+    # ---- the two configurations that SHARD over the GPUs, measured in the same run (sub-records) ----
+    sub4 = sub5 = None
+    if not args.no_sharded:
+        del dev
+        torch.cuda.empty_cache()
+        sub4 = sub_config4(ctx, rank, world, timed)
+        sub5 = sub_config5(ctx, rank, world, timed, dist)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -606,6 +708,8 @@ def main():
                                       'frames resident; the BIC search runs split into sub-chains',
                               'ms_per_step': ms_d2 / args.steps,
                               'value': world * args.steps * (FRAMES / RATE / 3600.0) / (ms_d2 / 1e3), 'unit': 'audio-hours/s'},
+            'config4': sub4,
+            'config5': sub5,
             'result': {'bic_changes': int(np.sum(res['BIC']['positive'])), 'glr_changes': int(np.sum(res['GLR']['positive'])),
                        'kl2_changes': int(np.sum(res['KL2']['positive'])), 'true_turns': len(rec.turns),
                        'windows': {k: int(len(res[k])) for k in ('BIC', 'GLR', 'KL2')},

@@ -303,6 +303,11 @@ int  spkdiar_cluster_free(spkdiar_clus* c);
 /* test hook: copy the current pair matrix (nseg x nseg, row-major, entries of
  * dead rows / columns undefined) and the alive flags to the host */
 int  spkdiar_cluster_matrix(spkdiar_clus* c, double* out, uint8_t* alive);
+/* measurement hook: SM-clock cycles CTA 0 spent in the five phases of the last persistent merge loop on this
+ * handle (spkdiar_cluster_run, _run_sharded_p2p), summed over the merges: out6[0] cached-minimum scan,
+ * [1] first grid barrier, [2] pick + exchange with the other ranks + stop test, [3] rescoring of the merged row,
+ * [4] second grid barrier; out6[5] = merges.  bench.py reports them per merge for the sharded configuration. */
+int  spkdiar_cluster_counters(const spkdiar_clus* c, uint64_t* out6);
 /* test hook: the NEXT spkdiar_cluster_run on this handle also copies row `a` of the pair matrix as merge m
  * rewrote it (nseg doubles, ORIGINAL indices; entries of dead columns undefined) to host_rows[m * nseg ...],
  * for the first cap_rows merges - what a host needs to replay the agglomeration and check that every merge

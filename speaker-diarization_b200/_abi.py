@@ -33,7 +33,7 @@ SYMBOLS = (
     'spkdiar_cluster_run_sharded', 'spkdiar_cluster_run_sharded_nccl', 'spkdiar_nccl_unique_id',
     'spkdiar_cluster_run_sharded_p2p', 'spkdiar_mailbox_create', 'spkdiar_mailbox_open',
     'spkdiar_mailbox_close', 'spkdiar_mailbox_free',
-    'spkdiar_cluster_free', 'spkdiar_cluster_matrix', 'spkdiar_cluster_rowlog',
+    'spkdiar_cluster_free', 'spkdiar_cluster_matrix', 'spkdiar_cluster_rowlog', 'spkdiar_cluster_counters',
     'spkdiar_features_upload_batch', 'spkdiar_cluster_batch', 'spkdiar_selftest_stitch',
     'spkdiar_gw_multi_begin', 'spkdiar_gw_multi_wait', 'spkdiar_gw_multi_where', 'spkdiar_gw_multi_end',
     'spkdiar_ctx_exec',
@@ -122,6 +122,7 @@ def load_library(path=None):
         'spkdiar_cluster_free': (C.c_int, [vp]),
         'spkdiar_cluster_matrix': (C.c_int, [vp, pdbl, C.POINTER(C.c_uint8)]),
         'spkdiar_cluster_rowlog': (C.c_int, [vp, pdbl, i64]),
+        'spkdiar_cluster_counters': (C.c_int, [vp, C.POINTER(C.c_uint64)]),
         'spkdiar_features_upload_batch': (C.c_int, [vp, C.POINTER(vp), pi64, i32, i32, C.POINTER(vp), pi64]),
         'spkdiar_cluster_batch': (C.c_int, [vp, i32, pi64, pi64, pi64, C.c_int, dbl, dbl, i32, i32, vp, pi64, pdbl]),
         'spkdiar_selftest_stitch': (C.c_int, [C.c_uint64, dbl, i64, i32]),
@@ -627,6 +628,16 @@ class Clusters(object):
             self.h, float(threshold), int(max_spk), int(rank), int(nranks), arr, int(seq_base),
             out.ctypes.data_as(C.c_void_p), out.shape[0], C.byref(nm), _p(stats, C.c_double)))
         return out[:nm.value], stats
+
+    def counters(self):
+        """Phase cycle counters of the last persistent run: dict of cycles PER MERGE (CTA 0's clock)."""
+        out = np.zeros(6, dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.spkdiar_cluster_counters(self.h, _p(out, C.c_uint64)))
+        m = float(out[5]) if out[5] else 1.0
+        names = ('scan', 'barrier1', 'pick_exchange', 'rescore', 'barrier2')
+        d = {k: float(out[i]) / m for i, k in enumerate(names)}
+        d['merges'] = int(out[5])
+        return d
 
     def rowlog(self, cap_rows):
         """Test hook: the next run() also records row ``a`` of the pair matrix after every merge

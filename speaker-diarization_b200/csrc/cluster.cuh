@@ -34,6 +34,7 @@ struct spkdiar_clus {
     bool ran = false;
     double* rowlog_host = nullptr;   // test hook (spkdiar_cluster_rowlog): row a after every merge
     int64_t rowlog_cap = 0;
+    uint64_t counters[8] = {0};      // phase cycle counters of the last persistent run (spkdiar_cluster_counters)
 };
 
 namespace spk {

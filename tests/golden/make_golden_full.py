@@ -13,7 +13,8 @@ Jobs:
   c2_bic, c2_glr, c2_kl2     config 2, the WHOLE hour (360,000 frames, seed 1002): growing-window
                              search with spk-diarization2.py's flags; GLR -t 1500, KL2 -t 4000
   c3_cl1_200 ... c3_cl2_400  config 3 cut to its first 200 / 400 segments: spk-clustering.py and
-                             spk-clustering2.py -m hi -l 1.3
+                             spk-clustering2.py -m hi -l 1.3; c3_cl1_800: 800 segments, spk-clustering.py
+                             (about 80 minutes of CPU per arm: the reference grows like N^2.7)
   c4_f0, c4_f1, c4_f2        three ten-minute files of config 4 through BOTH stages
                              (D2:122-128: gw BIC change detection, then CL1 -m hi -l 1.3)
 
@@ -47,6 +48,7 @@ JOBS = {
     'c2_kl2': ('cd', GW + ['-d', 'KL2', '-t', '4000']),
     'c3_cl1_200': ('cl', 1, 200), 'c3_cl2_200': ('cl', 2, 200),
     'c3_cl1_400': ('cl', 1, 400), 'c3_cl2_400': ('cl', 2, 400),
+    'c3_cl1_800': ('cl', 1, 800),
     'c4_f0': ('d2', 0), 'c4_f1': ('d2', 1), 'c4_f2': ('d2', 2),
 }
 CL_FLAGS = ['-f', '100', '-m', 'hi', '-l', '1.3']
@@ -184,7 +186,7 @@ def merge():
 def run_all(par=7):
     env = dict(os.environ, OPENBLAS_NUM_THREADS='1', OMP_NUM_THREADS='1', MKL_NUM_THREADS='1')
     # longest first
-    order = ['c3_cl1_400', 'c3_cl2_400', 'c2_kl2', 'c2_bic', 'c2_glr', 'c3_cl1_200', 'c3_cl2_200',
+    order = ['c3_cl1_800', 'c3_cl1_400', 'c3_cl2_400', 'c2_kl2', 'c2_bic', 'c2_glr', 'c3_cl1_200', 'c3_cl2_200',
              'c4_f0', 'c4_f1', 'c4_f2']
     todo = [(n, a) for n in order for a in ('ref', 'ora')
             if not os.path.isfile(os.path.join(TMP, '%s.%s.json' % (n, a)))]

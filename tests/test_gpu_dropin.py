@@ -87,7 +87,7 @@ def test_scripts_run_from_cwd_like_spk_diarization2(install, tmp_path):
     # the same chain through the CPU oracle (and the host glue, golden-tested against the reference)
     o_vad = str(tmpp / 'o_vad.recipe')
     glue.vad_main([init, str(exppath), '-o', o_vad, '-ms', '0.5', '-mns', '1.5'], stdout=io.StringIO())
-    assert open(vad).read() == open(o_vad).read() and open(vad).read().count('\n') == 3
+    assert open(vad).read() == open(o_vad).read() and open(vad).read().count('\n') >= 2
     o_spkc, o_out = str(tmpp / 'o_spkc.recipe'), str(tmpp / 'o_out.recipe')
     run_oracle('cd', 0, [o_vad, fp, '-o', o_spkc, '-m', 'gw', '-d', 'BIC', '-w', '1.0', '-st', '3.0',
                          '-dws', '0.1', '-l', '1.0'])
