@@ -81,7 +81,7 @@ __device__ __forceinline__ void cl_track(double d, unsigned long long* stat) {  
     atomicMin(stat + 1, cl_ord(d));
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 cl_init_records(const Stats st, const int64_t* __restrict__ seg, int64_t n,
                 double* __restrict__ rec) {
     const int64_t s = blockIdx.x;
@@ -89,7 +89,7 @@ cl_init_records(const Stats st, const int64_t* __restrict__ seg, int64_t n,
     for (int q = threadIdx.x; q < REC; q += blockDim.x) rec[s * REC + q] = w(q);
 }
 
-__global__ void __launch_bounds__(SC_THREADS, 3)
+static __global__ void __launch_bounds__(SC_THREADS, 3)
 cl_self_logdet(const double* rec, int64_t n, double* __restrict__ ld) {
     extern __shared__ __align__(16) unsigned char sc_smem[];
     WarpScratch* ws = reinterpret_cast<WarpScratch*>(sc_smem);
@@ -101,7 +101,7 @@ cl_self_logdet(const double* rec, int64_t n, double* __restrict__ ld) {
     }
 }
 
-__global__ void cl_fill_const(double* __restrict__ M, int64_t n, double offdiag, double diag) {
+static __global__ void cl_fill_const(double* __restrict__ M, int64_t n, double offdiag, double diag) {
     const int64_t total = n * n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / n, c = i - r * n;
@@ -133,7 +133,7 @@ __device__ __forceinline__ double cl_pair_distance(int metric, double lambda, co
 }
 
 // initial fill, spk-clustering.py:188-200 / spk-clustering2.py:180-184
-__global__ void __launch_bounds__(SC_THREADS, 3)
+static __global__ void __launch_bounds__(SC_THREADS, 3)
 cl_fill_pairs(const double* rec, const double* __restrict__ ld, int64_t n, int metric, double lambda,
               int variant, double* __restrict__ M, unsigned long long* stat) {
     extern __shared__ __align__(16) unsigned char sc_smem[];
@@ -449,7 +449,7 @@ __device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, i
 }
 
 // the merge loop as ONE persistent cooperative kernel (single GPU)
-__global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
+static __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
     extern __shared__ __align__(16) unsigned char cl_smem[];
     const ClSmem sm = cl_carve(cl_smem);
     __shared__ ClBest gbest;
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDev g) {
 
 // ---- the same two phases as separate launches (row-sharded run: the host exchanges the ranks'
 // candidates between them) ----
-__global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_argmin(const ClDev g, long long nm) {
+static __global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_argmin(const ClDev g, long long nm) {
     if (g.stopped && *((volatile int*)g.stopped)) return;
     extern __shared__ __align__(16) unsigned char cl_smem[];
     const ClSmem sm = cl_carve(cl_smem);
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_argmin(const ClDev g, 
     }
 }
 
-__global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_apply(const ClDev g, long long nm, int64_t a, int64_t b) {
+static __global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_apply(const ClDev g, long long nm, int64_t a, int64_t b) {
     extern __shared__ __align__(16) unsigned char cl_smem[];
     const ClSmem sm = cl_carve(cl_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_apply(const ClDev g, l
 
 // cl_shard_apply with the decision taken on the device: every thread picks the global minimum of
 // the gathered candidates (ndarray.argmin order) and evaluates the stop test of CL1:207-208
-__global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_apply_dev(const ClDev g, long long nm) {
+static __global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_apply_dev(const ClDev g, long long nm) {
     if (*((volatile int*)g.stopped)) return;
     ClBest best{__ldcg(&g.gathered[0].v), __ldcg((const long long*)&g.gathered[0].idx)};
     for (int r = 1; r < g.nranks; ++r)
@@ -721,7 +721,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_shard_apply_dev(const ClDev 
 }
 
 // initial fill of the pairs this rank owns (nranks > 1)
-__global__ void __launch_bounds__(SC_THREADS, 3)
+static __global__ void __launch_bounds__(SC_THREADS, 3)
 cl_fill_pairs_shard(const double* rec, const double* __restrict__ ld, int64_t n, int metric, double lambda,
                     int rank, int nranks, double* __restrict__ M, unsigned long long* stat) {
     extern __shared__ __align__(16) unsigned char sc_smem[];
@@ -745,7 +745,7 @@ cl_fill_pairs_shard(const double* rec, const double* __restrict__ ld, int64_t n,
 }
 
 // spk-clustering2.py:220: distances.max() over the compacted matrix (NaN propagates)
-__global__ void cl_alive_max(const double* __restrict__ M, const uint8_t* __restrict__ alive, int64_t n,
+static __global__ void cl_alive_max(const double* __restrict__ M, const uint8_t* __restrict__ alive, int64_t n,
                              unsigned long long* out /* [0]=ordered max, [1]=nan flag */) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / n, c = i - r * n;
@@ -762,8 +762,11 @@ inline size_t cl_smem_bytes(int64_t n) {
            + (size_t)((n + 31) / 32) * sizeof(uint32_t) + 16;
 }
 
-inline cudaError_t cluster_configure() {
+cudaError_t cluster_small_configure();         // cluster_small.cuh
+cudaError_t cluster_configure() {
     cudaError_t e = cudaFuncSetAttribute(cl_merge_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cluster_small_configure();
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(cl_shard_argmin, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;

@@ -48,7 +48,7 @@ inline size_t cl_batch_smem_bytes(int64_t nmax) {
            + 4 * sizeof(unsigned long long) + (size_t)((nmax + 31) / 32) * sizeof(uint32_t) + 16;
 }
 
-__global__ void __launch_bounds__(CL_THREADS, 1) cl_batch_kernel(const ClBatchDev g) {
+static __global__ void __launch_bounds__(CL_THREADS, 1) cl_batch_kernel(const ClBatchDev g) {
     extern __shared__ __align__(16) unsigned char cl_smem[];
     WarpScratch* ws = reinterpret_cast<WarpScratch*>(cl_smem);
     double* merged = reinterpret_cast<double*>(cl_smem + CL_WARPS * sizeof(WarpScratch));
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) cl_batch_kernel(const ClBatchDe
     }
 }
 
-inline cudaError_t cluster_batch_configure() {
+cudaError_t cluster_batch_configure() {
     return cudaFuncSetAttribute(cl_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 }
 

@@ -1,4 +1,9 @@
 // common.cuh - context, error plumbing and small helpers shared by the kernels.
+//
+// The library is built from three translation units that nvcc compiles side by side (spkdiar.cu: context,
+// statistics, batched scoring; spkdiar_gw.cu: the growing-window search; spkdiar_cluster.cu: the clustering
+// engines).  Every kernel is `static __global__` (each unit instantiates only what it launches), the shared
+// device code lives in the .cuh headers.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -148,6 +153,24 @@ struct DevBuf {                      // RAII device buffer from the context's ca
         return pool_alloc(ctx, count * sizeof(T) + 16, (void**)&p);
     }
 };
+
+// grid size of a throughput kernel: enough CTAs for the tasks, at most ctas_per_sm per (allowed) SM
+static inline int grid_for(const spkdiar_ctx* c, int64_t tasks, int per_cta, int ctas_per_sm) {
+    int64_t want = (tasks + per_cta - 1) / per_cta;
+    const int sms = c->sms_limit > 0 ? (c->sms < c->sms_limit ? c->sms : c->sms_limit) : c->sms;
+    const int64_t cap = (int64_t)sms * ctas_per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+static inline int check_metric(spkdiar_ctx* c, int metric) {
+    if (metric != SPKDIAR_GLR && metric != SPKDIAR_BIC && metric != SPKDIAR_KL2)
+        return set_err(c, SPKDIAR_E_ARG, "unknown metric %d", metric);
+    return SPKDIAR_OK;
+}
+// per-translation-unit kernel attributes (dynamic shared memory sizes), called once by spkdiar_create
+cudaError_t gw_configure();
+cudaError_t cluster_configure();
+cudaError_t cluster_batch_configure();
 
 __device__ __forceinline__ double d_nan() { return __longlong_as_double(0x7ff8000000000000LL); }
 __device__ __forceinline__ double d_inf() { return __longlong_as_double(0x7ff0000000000000LL); }

@@ -473,7 +473,7 @@ struct GwState {
 };
 
 template <bool KL2, bool SPLIT>
-__global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
+static __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g) {
     extern __shared__ __align__(16) unsigned char gw_smem[];
     GwPlan& plan = *reinterpret_cast<GwPlan*>(gw_smem);
     unsigned char* scratch_base = gw_smem + ((sizeof(GwPlan) + 15) & ~(size_t)15);
@@ -1085,7 +1085,7 @@ inline size_t gw_smem_bytes(bool kl2) {
            + sizeof(uint64_t) * GW_RING_STAGES + sizeof(long long) * 2 * GW_CHAIN_WARPS;
 }
 
-inline cudaError_t gw_configure() {
+cudaError_t gw_configure() {
     cudaError_t e = cudaFuncSetAttribute(gw_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)gw_smem_bytes(false));
     if (e != cudaSuccess) return e;

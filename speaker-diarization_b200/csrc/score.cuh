@@ -88,7 +88,7 @@ __device__ __forceinline__ double logdet_term(int term, int metric, const SrcX& 
 }
 
 // ---- windows of one recording: candidate k = (a, m, b) -----------------------------------
-__global__ void __launch_bounds__(SC_THREADS, 3)
+static __global__ void __launch_bounds__(SC_THREADS, 3)
 win_terms_kernel(const Stats st, const int64_t* __restrict__ a,
                  const int64_t* __restrict__ m, const int64_t* __restrict__ b,
                  int64_t ncand, int metric, double* __restrict__ terms) {
@@ -106,7 +106,7 @@ win_terms_kernel(const Stats st, const int64_t* __restrict__ a,
     }
 }
 
-__global__ void win_combine_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ m,
+static __global__ void win_combine_kernel(const int64_t* __restrict__ a, const int64_t* __restrict__ m,
                                    const int64_t* __restrict__ b, int64_t ncand, int metric,
                                    double lambda, const double* __restrict__ terms,
                                    double* __restrict__ out) {
@@ -237,7 +237,7 @@ __device__ __forceinline__ double kl2_finish(Kl2Scratch& k, int lane, double* t1
     return __dadd_rn(__dmul_rn(0.5, t1), __dmul_rn(0.5, t2));
 }
 
-__global__ void __launch_bounds__(SC_THREADS, 2)
+static __global__ void __launch_bounds__(SC_THREADS, 2)
 win_kl2_kernel(const Stats st, const float* __restrict__ x,
                const int64_t* __restrict__ a, const int64_t* __restrict__ m,
                const int64_t* __restrict__ b, int64_t ncand, double* __restrict__ out,
@@ -264,7 +264,7 @@ win_kl2_kernel(const Stats st, const float* __restrict__ x,
 
 // ---- sets of frame ranges (clusters given by the host) -----------------------------------
 // record of a set = sum over its ranges of (P[b] - P[a]), plain cluster record
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 set_records_kernel(const Stats st, const int64_t* __restrict__ off,
                    const int64_t* __restrict__ ra, const int64_t* __restrict__ rb,
                    int64_t nsets, double* __restrict__ rec) {
@@ -278,7 +278,7 @@ set_records_kernel(const Stats st, const int64_t* __restrict__ off,
 }
 
 // pair p scores record recX[p] against recY[p]
-__global__ void __launch_bounds__(SC_THREADS, 3)
+static __global__ void __launch_bounds__(SC_THREADS, 3)
 pair_terms_kernel(const double* recX, const double* recY, int64_t npairs, int metric,
                   double* __restrict__ terms) {
     extern __shared__ __align__(16) unsigned char sc_smem[];
@@ -295,7 +295,7 @@ pair_terms_kernel(const double* recX, const double* recY, int64_t npairs, int me
     }
 }
 
-__global__ void pair_combine_kernel(const double* __restrict__ recX, const double* __restrict__ recY,
+static __global__ void pair_combine_kernel(const double* __restrict__ recX, const double* __restrict__ recY,
                                     int64_t npairs, int metric, double lambda,
                                     const double* __restrict__ terms, double* __restrict__ out) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,7 +306,7 @@ __global__ void pair_combine_kernel(const double* __restrict__ recX, const doubl
                                    : glr_combine(N1, N2, t[0], t[1], t[2]);
 }
 
-__global__ void __launch_bounds__(SC_THREADS, 2)
+static __global__ void __launch_bounds__(SC_THREADS, 2)
 pair_kl2_kernel(const double* recX, const double* recY, const float* __restrict__ x,
                 const int64_t* __restrict__ off1, const int64_t* __restrict__ a1, const int64_t* __restrict__ b1,
                 const int64_t* __restrict__ off2, const int64_t* __restrict__ a2, const int64_t* __restrict__ b2,

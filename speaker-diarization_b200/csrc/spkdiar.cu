@@ -18,20 +18,10 @@
 #include "common.cuh"
 #include "stats.cuh"
 #include "score.cuh"
-#include "gw.cuh"
-#include "cluster.cuh"
-#include "cluster_batch.cuh"
 
 using namespace spk;
 
 static thread_local char g_create_err[512] = "";
-
-static int grid_for(const spkdiar_ctx* c, int64_t tasks, int per_cta, int ctas_per_sm) {
-    int64_t want = (tasks + per_cta - 1) / per_cta;
-    int64_t cap = (int64_t)(c->sms_limit > 0 ? std::min(c->sms, c->sms_limit) : c->sms) * ctas_per_sm;
-    if (want < 1) want = 1;
-    return (int)(want < cap ? want : cap);
-}
 
 extern "C" {
 
@@ -322,12 +312,6 @@ int spkdiar_stats_window(spkdiar_feat* f, int64_t a, int64_t b, double* out819, 
 
 // ---- K2 ---------------------------------------------------------------------------------
 
-static int check_metric(spkdiar_ctx* c, int metric) {
-    if (metric != SPKDIAR_GLR && metric != SPKDIAR_BIC && metric != SPKDIAR_KL2)
-        return set_err(c, SPKDIAR_E_ARG, "unknown metric %d", metric);
-    return SPKDIAR_OK;
-}
-
 int spkdiar_score_windows(spkdiar_feat* f, const int64_t* a, const int64_t* m, const int64_t* b,
                           int64_t ncand, int metric, double lambda, double* out_d, double* out_terms) {
     if (!f) return SPKDIAR_E_ARG;
@@ -437,6 +421,3 @@ int spkdiar_score_sets(spkdiar_feat* f, int64_t npairs,
 
 }  // extern "C"
 
-#include "abi_gw.inc"
-#include "abi_cluster.inc"
-#include "abi_batch.inc"

@@ -74,7 +74,7 @@ __device__ __forceinline__ void k1_shift_body(const float* __restrict__ x, int64
         shift[threadIdx.x] = (threadIdx.x < D39 && ns > 0) ? t / (double)ns : 0.0;
     }
 }
-__global__ void __launch_bounds__(1024) k1_shift(const float* __restrict__ x, int64_t n, double* __restrict__ shift) {
+static __global__ void __launch_bounds__(1024) k1_shift(const float* __restrict__ x, int64_t n, double* __restrict__ shift) {
     k1_shift_body(x, n, shift);
 }
 
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(1024) k1_shift(const float* __restrict__ x, in
 // the same recording uploaded alone.
 struct RecTab { int64_t base; int64_t n; };
 
-__global__ void __launch_bounds__(1024) k1_shift_batch(const float* __restrict__ x, const RecTab* __restrict__ tab,
+static __global__ void __launch_bounds__(1024) k1_shift_batch(const float* __restrict__ x, const RecTab* __restrict__ tab,
                                                        double* __restrict__ shift) {
     const RecTab t = tab[blockIdx.x];
     k1_shift_body(x + t.base * D39, t.n, shift + (int64_t)blockIdx.x * K1_XS);
@@ -167,7 +167,7 @@ __device__ __forceinline__ void k1_chunk_sums_body(const double* __restrict__ ti
     for (; t < t1; ++t) dd_add(hi, lo, tile[t * REC + q]);
     chunk_tot[idx] = make_double2(hi, lo);
 }
-__global__ void __launch_bounds__(128) k1_chunk_sums(const double* __restrict__ tile, int64_t ntiles,
+static __global__ void __launch_bounds__(128) k1_chunk_sums(const double* __restrict__ tile, int64_t ntiles,
                                                      double2* __restrict__ chunk_tot) {
     k1_chunk_sums_body(tile, ntiles, chunk_tot);
 }
@@ -198,7 +198,7 @@ __device__ __forceinline__ void k1_chunk_scan_body(const double* __restrict__ ti
     // the thread that owns the last block also writes the grand total
     if (write_total && t1 == ntiles && t0 < ntiles) C[ntiles * REC + q] = make_double2(hi, lo);
 }
-__global__ void __launch_bounds__(128) k1_chunk_scan(const double* __restrict__ tile, int64_t ntiles,
+static __global__ void __launch_bounds__(128) k1_chunk_scan(const double* __restrict__ tile, int64_t ntiles,
                                                      const double2* __restrict__ chunk_tot,
                                                      double2* __restrict__ C) {
     k1_chunk_scan_body(tile, ntiles, chunk_tot, C, true);
@@ -206,14 +206,14 @@ __global__ void __launch_bounds__(128) k1_chunk_scan(const double* __restrict__ 
 // packed batch: blockIdx.y = recording.  The scan runs over ceil(n / K1_TILE) blocks exactly as for
 // a recording uploaded alone; the total lands in the recording's own extra block when n is a
 // multiple of K1_TILE and is not written otherwise (the slot would be the next recording's zero).
-__global__ void __launch_bounds__(128) k1_chunk_sums_batch(const double* __restrict__ tile, const RecTab* __restrict__ tab,
+static __global__ void __launch_bounds__(128) k1_chunk_sums_batch(const double* __restrict__ tile, const RecTab* __restrict__ tab,
                                                            double2* __restrict__ chunk_tot) {
     const RecTab t = tab[blockIdx.y];
     const int64_t nt = (t.n + K1_TILE - 1) / K1_TILE;
     if (nt == 0) return;
     k1_chunk_sums_body(tile + (t.base / K1_TILE) * REC, nt, chunk_tot + (int64_t)blockIdx.y * K1_CHUNKS * REC);
 }
-__global__ void __launch_bounds__(128) k1_chunk_scan_batch(const double* __restrict__ tile, const RecTab* __restrict__ tab,
+static __global__ void __launch_bounds__(128) k1_chunk_scan_batch(const double* __restrict__ tile, const RecTab* __restrict__ tab,
                                                            const double2* __restrict__ chunk_tot,
                                                            double2* __restrict__ C) {
     const RecTab t = tab[blockIdx.y];
@@ -256,14 +256,14 @@ __device__ __forceinline__ void k1_tile_write_body(const float* __restrict__ x, 
     // a recording that ends exactly on a block boundary still needs its last (zero) record
     if (valid == K1_TILE && f0 + K1_TILE == n) __stcs(out + (int64_t)K1_TILE * REC, 0.0);
 }
-__global__ void __launch_bounds__(K1_THREADS) k1_tile_write(const float* __restrict__ x, int64_t n,
+static __global__ void __launch_bounds__(K1_THREADS) k1_tile_write(const float* __restrict__ x, int64_t n,
                                                             const double* __restrict__ shift,
                                                             double* __restrict__ tile,
                                                             double* __restrict__ P) {
     k1_tile_write_body(x, n, shift, tile, P);
 }
 // packed batch: blockIdx.y = recording, blockIdx.x = block of the recording (n / K1_TILE + 1 of them)
-__global__ void __launch_bounds__(K1_THREADS) k1_tile_write_batch(const float* __restrict__ x,
+static __global__ void __launch_bounds__(K1_THREADS) k1_tile_write_batch(const float* __restrict__ x,
                                                                   const RecTab* __restrict__ tab,
                                                                   const double* __restrict__ shift,
                                                                   double* __restrict__ tile,
