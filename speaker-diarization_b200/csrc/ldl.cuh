@@ -209,32 +209,47 @@ __device__ __forceinline__ double fast_rcp(double a) {
 
 // One elimination step.  On entry the lane already holds what it needs of column C
 // (read from the strip by the previous step): the pivot, the entries vr[] of its own
-// rows and vk[] of its own columns, and q = 1 / pivot is on its way.  The step
-// (1) updates column C + 1 and publishes it, (2) reads its part of column C + 1 back
-// and starts the next reciprocal, (3) applies the rest of the rank-1 update.
-// (Measured on B200, one warp alone: 195 cycles per step, of which about 105 are the
-// dependent chain strip round trip -> reciprocal -> multiply -> FMA and the rest is
-// fp64 issue time that the static schedule does not overlap with the chain; a variant
-// that takes the next pivot by warp shuffle to shorten the chain was slower.)
+// rows and vk[] of its own columns, q = 1 / pivot - and, for the LOOK-AHEAD, vnx = M(C+1, C)
+// and dn = the diagonal entry (C+1, C+1) as it stands before this step.  With those every lane
+// computes the NEXT pivot itself, npiv = dn - (vnx q) vnx (the very fma the owner of that entry
+// executes: same bits), and starts its reciprocal at once; the dependent chain of a step is then
+// q -> multiply -> fma -> reciprocal (about 63 cycles) next to, not behind, the strip round trip
+// multiply -> fma -> store -> __syncwarp -> load (about 55).  The step
+// (1) updates column C + 1 and the diagonal entry (C+2, C+2) and publishes them (the diagonal in
+//     strip slot VS - 1), (2) reads its part of column C + 1 back, (3) applies the rest of the
+// rank-1 update.
+// (Measured on B200, one warp alone, before the look-ahead: 195 cycles per step, of which about
+// 105 were the chain strip round trip -> reciprocal -> multiply -> FMA; a variant that takes the
+// next pivot by warp shuffle was slower.)
 template <int D, bool STORE, int C>
 struct LdlStep {
     using G = Grid<D>;
     static __device__ __forceinline__ void run(double (&a)[G::NSLOT], LdlScratch& w, int lane, int i, int j,
                                                const double (&vr)[G::NRI], const double (&vk)[G::NKJ],
-                                               double piv, double q,
+                                               double piv, double q, double vnx, double dn,
                                                double& p0, double& p1, bool& bad, double* Lsm, double* pinv) {
         constexpr int ri_a = (C + 1) / G::PR;          // first local row that can hold a row > C
         constexpr int kj_a = (C + 1) / G::PC;          // first local column that can hold a column > C
         constexpr int kn = (C + 1) / G::PC, jn = (C + 1) % G::PC;     // local column / owner lanes of column C + 1
+        // the diagonal entry (C+2, C+2): local column / row and owner lane
+        constexpr int k2 = (C + 2) / G::PC, j2 = (C + 2) % G::PC, r2 = (C + 2) / G::PR, i2 = (C + 2) % G::PR;
+        constexpr bool ahead = C + 2 < D;
+        constexpr bool extra = ahead && k2 != kn;      // it does not lie in the local column updated first
         double* vn = w.v[(C + 1) & 1];
         bad |= !(piv > 0.0);
         if ((C & 31) == lane) { if (C < 32) p0 = piv; else p1 = piv; }
+        // look-ahead: the next pivot and its reciprocal, from values every lane holds
+        double npiv = 1.0, nq = 1.0;
+        if (C + 1 < D) {
+            npiv = fma(-(vnx * q), vnx, dn);
+            nq = fast_rcp(npiv);
+        }
         double lr[G::NRI];
 #pragma unroll
         for (int ri = ri_a; ri < G::NRI; ++ri) lr[ri] = vr[ri] * q;
-        double nvr[G::NRI], nvk[G::NKJ], npiv = 1.0, nq = 1.0;
+        double nvr[G::NRI], nvk[G::NKJ], nvnx = 0.0, ndn = 1.0;
         if (C + 1 < D) {
-            // (1) column C + 1 first: update it and hand it over at once
+            // (1) column C + 1 first (and the diagonal after it): update and hand over at once
 #pragma unroll
             for (int ri = (ri_a > G::ri_first(kn) ? ri_a : G::ri_first(kn)); ri < G::NRI; ++ri) {
                 const int r = i + G::PR * ri;
@@ -242,22 +257,25 @@ struct LdlStep {
                 a[G::slot(kn, ri)] = m;
                 st_shared_if(j == jn && r > C && r < D, vn + r, m);
             }
+            if (extra) a[G::slot(k2, r2)] = fma(-lr[r2], vk[k2], a[G::slot(k2, r2)]);
+            if (ahead) st_shared_if(i == i2 && j == j2, vn + (VS - 1), a[G::slot(k2, r2)]);
             __syncwarp();
             // (2) what the next step needs of column C + 1
             constexpr int ri_n = (C + 2) / G::PR, kj_n = (C + 2) / G::PC;
-            npiv = vn[C + 1];
 #pragma unroll
             for (int ri = ri_n; ri < G::NRI; ++ri) nvr[ri] = vn[i + G::PR * ri];
 #pragma unroll
             for (int kj = kj_n; kj < G::NKJ; ++kj) nvk[kj] = vn[j + G::PC * kj];
-            nq = fast_rcp(npiv);
+            if (ahead) { nvnx = vn[C + 2]; ndn = vn[VS - 1]; }
             // (3) the rest of the update of step C
 #pragma unroll
             for (int kj = kj_a; kj < G::NKJ; ++kj) {
                 if (kj == kn) continue;
 #pragma unroll
-                for (int ri = (ri_a > G::ri_first(kj) ? ri_a : G::ri_first(kj)); ri < G::NRI; ++ri)
+                for (int ri = (ri_a > G::ri_first(kj) ? ri_a : G::ri_first(kj)); ri < G::NRI; ++ri) {
+                    if (extra && kj == k2 && ri == r2) continue;        // done in (1)
                     a[G::slot(kj, ri)] = fma(-lr[ri], vk[kj], a[G::slot(kj, ri)]);
+                }
             }
         }
         if (STORE) {
@@ -269,7 +287,7 @@ struct LdlStep {
             }
             st_shared_if(lane == 0, pinv + C, q);
         }
-        LdlStep<D, STORE, C + 1>::run(a, w, lane, i, j, nvr, nvk, npiv, nq, p0, p1, bad, Lsm, pinv);
+        LdlStep<D, STORE, C + 1>::run(a, w, lane, i, j, nvr, nvk, npiv, nq, nvnx, ndn, p0, p1, bad, Lsm, pinv);
     }
 };
 template <int D, bool STORE>
@@ -277,20 +295,22 @@ struct LdlStep<D, STORE, D> {
     using G = Grid<D>;
     static __device__ __forceinline__ void run(double (&)[G::NSLOT], LdlScratch&, int, int, int,
                                                const double (&)[G::NRI], const double (&)[G::NKJ], double, double,
-                                               double&, double&, bool&, double*, double*) {}
+                                               double, double, double&, double&, bool&, double*, double*) {}
 };
 
 template <int D, bool STORE>
 __device__ __forceinline__ double ldl_logdet(double (&a)[Grid<D>::NSLOT], LdlScratch& w, int lane,
                                              double* Lsm = nullptr, double* pinv = nullptr) {
     using G = Grid<D>;
+    static_assert(VS - 1 >= D, "the strip needs a spare slot for the look-ahead diagonal");
     double p0 = 1.0, p1 = 1.0;             // pivots c == lane and c == lane + 32
     bool bad = false;
     const int i = lane >> 3, j = lane & 7;
     __syncwarp();                          // the strips may still be read by a slower lane of the previous task
 #pragma unroll
-    for (int ri = 0; ri < G::NRI; ++ri)    // prologue: publish column 0 and read it back
+    for (int ri = 0; ri < G::NRI; ++ri)    // prologue: publish column 0 (and the diagonal entry (1, 1)), read back
         st_shared_if(j == 0 && i + G::PR * ri < D, w.v[0] + i + G::PR * ri, a[G::slot(0, ri)]);
+    if (D > 1) st_shared_if(i == 1 % G::PR && j == 1 % G::PC, w.v[0] + (VS - 1), a[G::slot(1 / G::PC, 1 / G::PR)]);
     __syncwarp();
     double vr[G::NRI], vk[G::NKJ];
     const double piv = w.v[0][0];
@@ -298,7 +318,8 @@ __device__ __forceinline__ double ldl_logdet(double (&a)[Grid<D>::NSLOT], LdlScr
     for (int ri = 0; ri < G::NRI; ++ri) vr[ri] = w.v[0][i + G::PR * ri];
 #pragma unroll
     for (int kj = 0; kj < G::NKJ; ++kj) vk[kj] = w.v[0][j + G::PC * kj];
-    LdlStep<D, STORE, 0>::run(a, w, lane, i, j, vr, vk, piv, fast_rcp(piv), p0, p1, bad, Lsm, pinv);
+    const double vnx = D > 1 ? w.v[0][1] : 0.0, dn = D > 1 ? w.v[0][VS - 1] : 1.0;
+    LdlStep<D, STORE, 0>::run(a, w, lane, i, j, vr, vk, piv, fast_rcp(piv), vnx, dn, p0, p1, bad, Lsm, pinv);
     double s = log(p0);
     if (D > 32) s += log(p1);
 #pragma unroll
