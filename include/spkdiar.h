@@ -314,6 +314,39 @@ int  spkdiar_cluster_counters(const spkdiar_clus* c, uint64_t* out6);
  * was ndarray.argmin of the live matrix (spk-clustering.py:203-205).  cap_rows = 0 switches it off. */
 int  spkdiar_cluster_rowlog(spkdiar_clus* c, double* host_rows, int64_t cap_rows);
 
+/* ---- host replay of spk-diarization2.py's two calls, per recording (no device work) -----------
+ * Replaces the text side of `spk-change-detection.py ... -m gw` + `spk-clustering.py -m hi` as
+ * spk-diarization2.py:122-128 chains them: recipe parsing (spk-change-detection.py:11-28), one chain per run
+ * of equal lna (370-374), a recipe line per detected change (252-256, 286-288 through write_recipe_line,
+ * 46-69: LNA renaming, Python-2 str(float)), the clustering stage reading that text back into one cluster per
+ * line (spk-clustering.py:263-283), merges applied to the speaker lists and the turns written smallest first
+ * (216-220, 243-260).  The window records / merges come from spkdiar_gw_run / spkdiar_cluster_batch.
+ * Anything this unit does not reproduce to the byte (non-ASCII text, exponents or signs in a time field,
+ * several wavs in one recipe) is answered with SPKDIAR_E_UNSUPPORTED and text from spkdiar_replay_error():
+ * the caller then runs the general (Python) replay of that recording.  Handles are independent of contexts
+ * and of each other (any thread). */
+typedef struct spkdiar_replay spkdiar_replay;
+/* parses the recipe text (lines separated by '\n').  *out is set whenever memory could be had - also together
+ * with SPKDIAR_E_UNSUPPORTED (read the message, then free it). */
+int  spkdiar_replay_create(double rate, const char* recipe_text, int64_t len, spkdiar_replay** out);
+int  spkdiar_replay_free(spkdiar_replay* r);
+const char* spkdiar_replay_error(const spkdiar_replay* r);
+/* out6 = parsed lines, chains, 1 if all lines name one wav, turns written by _segment, speakers after
+ * _cluster, windows replayed */
+int  spkdiar_replay_info(const spkdiar_replay* r, int64_t* out6);
+/* the chains spkdiar_gw_run is to search: [base + a, base + b) per chain, frames clamped to nframes */
+int  spkdiar_replay_chains(const spkdiar_replay* r, int64_t nframes, int64_t base, int64_t* seg_a,
+                           int64_t* seg_b, int64_t cap);
+/* window records of this recording's chains: chain k = win[win_first[k] .. win_first[k + 1]) */
+int  spkdiar_replay_segment(spkdiar_replay* r, const spkdiar_gw_window* win, const int64_t* win_first);
+/* the initial clusters of the clustering stage, one per line of the segmentation recipe */
+int  spkdiar_replay_turns(const spkdiar_replay* r, int64_t nframes, int64_t base, int64_t* seg_a,
+                          int64_t* seg_b, int64_t cap);
+/* the merge sequence (compacted indices, as spkdiar_cluster_run returns them) -> clustered recipe */
+int  spkdiar_replay_cluster(spkdiar_replay* r, const spkdiar_merge* merges, int64_t nmerges);
+/* which = 0: segmentation recipe (after _segment), 1: clustered recipe (after _cluster); owned by r */
+const char* spkdiar_replay_text(const spkdiar_replay* r, int32_t which, int64_t* len);
+
 #ifdef __cplusplus
 }
 #endif

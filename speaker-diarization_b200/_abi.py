@@ -37,6 +37,9 @@ SYMBOLS = (
     'spkdiar_features_upload_batch', 'spkdiar_cluster_batch', 'spkdiar_selftest_stitch',
     'spkdiar_gw_multi_begin', 'spkdiar_gw_multi_wait', 'spkdiar_gw_multi_where', 'spkdiar_gw_multi_end',
     'spkdiar_ctx_exec',
+    'spkdiar_replay_create', 'spkdiar_replay_free', 'spkdiar_replay_error', 'spkdiar_replay_info',
+    'spkdiar_replay_chains', 'spkdiar_replay_segment', 'spkdiar_replay_turns', 'spkdiar_replay_cluster',
+    'spkdiar_replay_text',
 )
 
 
@@ -131,6 +134,15 @@ def load_library(path=None):
         'spkdiar_gw_multi_where': (C.c_int, [vp, i32, C.POINTER(vp), C.POINTER(i32)]),
         'spkdiar_gw_multi_end': (C.c_int, [vp]),
         'spkdiar_ctx_exec': (C.c_int, [vp, vp, i32]),
+        'spkdiar_replay_create': (C.c_int, [dbl, C.c_char_p, i64, C.POINTER(vp)]),
+        'spkdiar_replay_free': (C.c_int, [vp]),
+        'spkdiar_replay_error': (C.c_char_p, [vp]),
+        'spkdiar_replay_info': (C.c_int, [vp, pi64]),
+        'spkdiar_replay_chains': (C.c_int, [vp, i64, i64, pi64, pi64, i64]),
+        'spkdiar_replay_segment': (C.c_int, [vp, vp, pi64]),
+        'spkdiar_replay_turns': (C.c_int, [vp, i64, i64, pi64, pi64, i64]),
+        'spkdiar_replay_cluster': (C.c_int, [vp, vp, i64]),
+        'spkdiar_replay_text': (vp, [vp, i32, pi64]),
     }
     for name, (res, args) in proto.items():
         fn = getattr(lib, name)
@@ -151,6 +163,95 @@ def nccl_unique_id():
     if rc != 0:
         raise SpkdiarError(rc, 'NCCL is not available (libnccl.so.2 could not be loaded)')
     return buf.raw
+
+
+class ReplayUnsupported(Exception):
+    """The native replay does not reproduce this recording to the byte (``SPKDIAR_E_UNSUPPORTED``):
+    run the general Python replay (``Detector`` / ``Clusterer``) instead."""
+
+
+class Replay(object):
+    """``spkdiar_replay``: one recording through the text side of spk-diarization2.py:122-128 in
+    native code - recipe text in, chains for the growing-window search, window records ->
+    segmentation recipe, initial clusters, merge sequence -> clustered recipe.  Host only (no
+    context, no device); the numeric results come from ``Features.gw_run`` / ``cluster_batch``."""
+
+    def __init__(self, rate, lines):
+        """``lines``: the recipe as a list of text lines (as ``readlines`` returns them)."""
+        self.lib = load_library()
+        self.h = None
+        text = ''.join(lines)
+        # an element that is not exactly one physical line is one "line" to the reference's searches
+        if text.count('\n') != sum(1 for l in lines if l.endswith('\n')) or \
+                any(not l.endswith('\n') for l in lines[:-1]):
+            raise ReplayUnsupported('recipe elements are not single lines')
+        try:
+            raw = text.encode('ascii')
+        except UnicodeEncodeError:
+            raise ReplayUnsupported('non-ASCII recipe text')
+        h = C.c_void_p()
+        rc = self.lib.spkdiar_replay_create(float(rate), raw, len(raw), C.byref(h))
+        self.h = h if h.value else None
+        self._check(rc)
+        info = self.info()
+        self.nlines, self.nchains, self.single_wav = int(info[0]), int(info[1]), bool(info[2])
+
+    def _check(self, rc):
+        if rc == 0:
+            return
+        text = (self.lib.spkdiar_replay_error(self.h) or b'').decode() if self.h else 'no handle'
+        if rc == -5:
+            raise ReplayUnsupported(text)
+        raise SpkdiarError(rc, text)
+
+    def info(self):
+        out = np.zeros(6, dtype=np.int64)
+        self._check(self.lib.spkdiar_replay_info(self.h, _p(out, C.c_int64)))
+        return out
+
+    def chains(self, nframes, base=0, seg_a=None, seg_b=None):
+        """-> (seg_a, seg_b) of this recording's chains, positions offset by ``base`` (the
+        recording's first row in a packed batch); writes into the given int64 views if any."""
+        if seg_a is None:
+            seg_a, seg_b = np.zeros(self.nchains, dtype=np.int64), np.zeros(self.nchains, dtype=np.int64)
+        self._check(self.lib.spkdiar_replay_chains(self.h, int(nframes), int(base), _p(seg_a, C.c_int64),
+                                                   _p(seg_b, C.c_int64), seg_a.shape[0]))
+        return seg_a, seg_b
+
+    def segment(self, win, first):
+        """``win``: window records (GW_WINDOW_DTYPE array), ``first``: int64 array with this
+        recording's nchains + 1 offsets into ``win``.  -> number of turns written."""
+        first = np.ascontiguousarray(first, dtype=np.int64)
+        if first.shape[0] != self.nchains + 1:
+            raise SpkdiarError(-2, 'win_first needs %d entries' % (self.nchains + 1))
+        self._check(self.lib.spkdiar_replay_segment(self.h, win.ctypes.data_as(C.c_void_p), _p(first, C.c_int64)))
+        return int(self.info()[3])
+
+    def turns(self, nframes, nturns, base=0, seg_a=None, seg_b=None):
+        if seg_a is None:
+            seg_a, seg_b = np.zeros(nturns, dtype=np.int64), np.zeros(nturns, dtype=np.int64)
+        self._check(self.lib.spkdiar_replay_turns(self.h, int(nframes), int(base), _p(seg_a, C.c_int64),
+                                                  _p(seg_b, C.c_int64), seg_a.shape[0]))
+        return seg_a, seg_b
+
+    def cluster(self, merges):
+        """``merges``: MERGE_DTYPE array (compacted indices).  -> number of speakers."""
+        merges = np.ascontiguousarray(merges, dtype=MERGE_DTYPE)
+        self._check(self.lib.spkdiar_replay_cluster(self.h, merges.ctypes.data_as(C.c_void_p), merges.shape[0]))
+        return int(self.info()[4])
+
+    def text(self, which):
+        n = C.c_int64(0)
+        ptr = self.lib.spkdiar_replay_text(self.h, int(which), C.byref(n))
+        return C.string_at(ptr, n.value).decode('ascii') if ptr else ''
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.spkdiar_replay_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        self.close()
 
 
 class _Serialised(object):
@@ -193,9 +294,21 @@ class Context(object):
             raise SpkdiarError(rc, (self.lib.spkdiar_last_error(self.h) or b'').decode())
 
     def close(self):
+        for extra in getattr(self, '_lanes', []):
+            extra.close()
+        self._lanes = []
         if getattr(self, 'h', None):
             self.lib.spkdiar_destroy(self.h)
             self.h = None
+
+    def lane_contexts(self, n):
+        """``n`` further contexts (own streams) on this context's device, created on first use and
+        closed with it: the extra lanes of ``corpus.diarize_batches``."""
+        lanes = getattr(self, '_lanes', [])
+        while len(lanes) < n:
+            lanes.append(Context(self.device))
+        self._lanes = lanes
+        return lanes[:n]
 
     def __enter__(self):
         return self
@@ -205,7 +318,8 @@ class Context(object):
 
     @property
     def launches(self):
-        return int(self.lib.spkdiar_launch_count(self.h))
+        """Kernels launched on this context and on its lane contexts."""
+        return int(self.lib.spkdiar_launch_count(self.h)) + sum(c.launches for c in getattr(self, '_lanes', []))
 
     @property
     def sm_count(self):
@@ -498,14 +612,19 @@ class FeaturePack(Features):
         """``problems[r]``: list of (a, b) frame ranges of recording r, the initial clusters of
         one ``spk_cluster_hi`` run.  One launch, one CTA per problem.  -> per problem
         (merges, stats[4]) exactly as ``view(r).cluster(...).run(...)`` returns them."""
-        first = np.zeros(len(problems) + 1, dtype=np.int64)
-        seg_a, seg_b = [], []
+        rows = []
         for r, segs in enumerate(problems):
-            for a, b in segs:
-                seg_a.append(self.base[r] + int(a))
-                seg_b.append(self.base[r] + int(b))
-            first[r + 1] = len(seg_a)
-        seg_a, seg_b = _i64(seg_a), _i64(seg_b)
+            rows.append((_i64([self.base[r] + int(a) for a, _ in segs]), _i64([self.base[r] + int(b) for _, b in segs])))
+        return self.cluster_batch_rows(rows, metric, lambdac, threshold, max_spk, variant)
+
+    def cluster_batch_rows(self, problems, metric, lambdac=1.3, threshold=0.0, max_spk=0, variant=1):
+        """The same with ``problems[p]`` = (seg_a, seg_b) int64 arrays in PACKED frame rows (any
+        recording of the pack, in any order)."""
+        first = np.zeros(len(problems) + 1, dtype=np.int64)
+        for p, (sa, _) in enumerate(problems):
+            first[p + 1] = first[p] + len(sa)
+        seg_a = _i64(np.concatenate([sa for sa, _ in problems])) if problems else np.zeros(0, dtype=np.int64)
+        seg_b = _i64(np.concatenate([sb for _, sb in problems])) if problems else np.zeros(0, dtype=np.int64)
         out = np.zeros(max(len(seg_a), 1), dtype=MERGE_DTYPE)
         nm = np.zeros(max(len(problems), 1), dtype=np.int64)
         stats = np.zeros((max(len(problems), 1), 4))

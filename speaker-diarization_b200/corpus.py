@@ -52,149 +52,248 @@ def diarize_recording(ctx, recipe_lines, frames_loader, frame_rate=125, threshol
     return seg.getvalue(), out.getvalue(), summary
 
 
+class _PythonRec(object):
+    """One recording of a device batch replayed by the general Python classes (``Detector`` /
+    ``Clusterer``): every recipe the scripts accept, at about 0.7 ms of host time per ten minutes."""
+
+    def __init__(self, ctx, lines, frame_rate, threshold):
+        from . import change_detection as pcd
+        self.ctx, self.rate, self.threshold = ctx, frame_rate, threshold
+        self.parsed = recipe_mod.parse(lines)
+        self.det = pcd.Detector(frame_rate, threshold=threshold, ctx=ctx, **D2_CHANGE)
+
+    def chains(self, view):
+        """-> (seg_a, seg_b): the chains of this recording in packed frame rows."""
+        import numpy as np
+        self.view = view
+        self.groups = self.det.gw_chains(self.parsed, lambda l: view)
+        flat = [c for _, ch in self.groups for c in ch]
+        return (np.array([view.off + int(a) for a, _ in flat], dtype=np.int64),
+                np.array([view.off + int(b) for _, b in flat], dtype=np.int64))
+
+    def segment(self, win, first, chain0=0):
+        """``win``: the records of the whole launch, ``first``: this recording's offsets into it,
+        ``chain0``: the launch's number of this recording's first chain.
+        -> (seg_a, seg_b) of the initial clusters of the clustering stage, packed frame rows."""
+        import numpy as np
+        from . import clustering as pcl
+        det, v = self.det, self.view
+        c0 = 0
+        for feat, ch in self.groups:                         # usually one group: one wav per recipe
+            lo, hi = int(first[c0]), int(first[c0 + len(ch)])
+            sub = win[lo:hi].copy()
+            sub['chain'] -= chain0 + c0
+            det.prefetch(feat, ch, (sub, first[c0:c0 + len(ch) + 1] - first[c0]))
+            c0 += len(ch)
+        seg = io.StringIO()
+        det.writer.record = []
+        det.detect_changes(self.parsed, seg, loader=lambda l: v)
+        self.seg_text = seg.getvalue()
+        seg_lines = self.seg_text.splitlines(True)
+        # the clustering stage reads the segmentation RECIPE (text, times rounded to 12 digits): the same
+        # values without the regular-expression searches
+        self.seg_parsed = recipe_mod.lines_from_records(det.writer.record, seg_lines)
+        self.cl = pcl.Clusterer(self.rate, variant=1, threshold=self.threshold, ctx=self.ctx, **D2_CLUSTER)
+        self.problem = self.cl.initial_segments(self.seg_parsed, v.n)
+        self.nturns = len(seg_lines)
+        return (np.array([v.off + a for a, _ in self.problem], dtype=np.int64),
+                np.array([v.off + b for _, b in self.problem], dtype=np.int64))
+
+    def finish(self, merged):
+        """``merged``: (merges, stats) of this recording's clustering problem, or None without turns."""
+        v = self.view
+        if merged is not None:
+            self.cl.prefetch(v, self.problem, merged)
+        clu = io.StringIO()
+        self.cl.process_recipe(self.seg_parsed, clu, loader=lambda l: v)
+        summary = dict(turns=self.nturns, speakers=len(self.cl.speakers), windows=self.det.windows_visited,
+                       merges=len(self.cl.merges))
+        return self.seg_text, clu.getvalue(), summary
+
+    def close(self):
+        pass
+
+
+class _NativeRec(object):
+    """The same three steps through ``spkdiar_replay_*`` (csrc/spkdiar_replay.cu): native code,
+    tens of microseconds per recording.  Raises ``_abi.ReplayUnsupported`` for what it does not
+    reproduce to the byte; the job then replays that recording with ``_PythonRec``."""
+
+    def __init__(self, lines, frame_rate):
+        from . import _abi
+        self.rp = _abi.Replay(frame_rate, lines)
+        if not self.rp.single_wav or self.rp.nchains == 0:
+            self.rp.close()
+            raise _abi.ReplayUnsupported('several wavs or no line in one recipe')
+
+    def chains(self, view):
+        self.view = view
+        return self.rp.chains(view.n, view.off)
+
+    def segment(self, win, first, chain0=0):
+        self.nturns = self.rp.segment(win, first)
+        return self.rp.turns(self.view.n, self.nturns, self.view.off)
+
+    def finish(self, merged):
+        info0 = self.rp.info()
+        nspk = self.rp.cluster(merged[0]) if merged is not None else 0
+        summary = dict(turns=self.nturns, speakers=nspk, windows=int(info0[5]),
+                       merges=len(merged[0]) if merged is not None else 0)
+        return self.rp.text(0), self.rp.text(1), summary
+
+    def close(self):
+        self.rp.close()
+
+
 class _BatchJob(object):
     """One device batch on its way through the four stages of ``diarize_batch``:
     A (device) packed upload + statistics + ONE growing-window launch over every chain,
     B (host)   replay of the window records into segmentation recipes,
     C (device) ONE clustering launch, one CTA per recording,
-    D (host)   replay of the merge sequences into clustered recipes."""
+    D (host)   replay of the merge sequences into clustered recipes.
+    The host stages run in native code (``_NativeRec``) unless ``native=False`` or a recording
+    needs the general replay (``_PythonRec``); results are identical."""
 
-    def __init__(self, ctx, batch, frame_rate, threshold):
-        from . import change_detection as pcd
+    def __init__(self, ctx, batch, frame_rate, threshold, native=True):
+        from . import _abi
         self.ctx, self.batch, self.rate, self.threshold = ctx, batch, frame_rate, threshold
-        self.parsed = [recipe_mod.parse(lines) for lines, _ in batch]
-        self.dets = [pcd.Detector(frame_rate, threshold=threshold, ctx=ctx, **D2_CHANGE) for _ in batch]
+        self.recs = []
+        for lines, _ in batch:
+            rec = None
+            if native:
+                try:
+                    rec = _NativeRec(lines, frame_rate)
+                except _abi.ReplayUnsupported:
+                    rec = None
+            self.recs.append(rec if rec is not None else _PythonRec(ctx, lines, frame_rate, threshold))
         self.pack = None
 
+    def _python_again(self, r):
+        """Recording r left the native replay: the general one takes over from the start."""
+        self.recs[r].close()
+        rec = _PythonRec(self.ctx, self.batch[r][0], self.rate, self.threshold)
+        sa, sb = rec.chains(self.views[r])
+        c0, c1 = self.owner[r], self.owner[r + 1]
+        if sa.tolist() != self.seg_a[c0:c1].tolist() or sb.tolist() != self.seg_b[c0:c1].tolist():
+            raise RuntimeError('native and Python replay disagree on the chains of recording %d' % r)
+        self.recs[r] = rec
+        return rec
+
     def stage_a(self):
+        import numpy as np
+        from . import change_detection as pcd
         self.pack = self.ctx.upload_batch([frames() if callable(frames) else frames for _, frames in self.batch])
         self.views = [self.pack.view(r) for r in range(len(self.batch))]
-        self.groups = [det.gw_chains(rec, lambda l, v=v: v)
-                       for det, rec, v in zip(self.dets, self.parsed, self.views)]
-        chains = [[c for _, ch in grp for c in ch] for grp in self.groups]
-        d0 = self.dets[0]
-        self.gw = self.pack.gw_run_batch(chains, d0.rate, d0.winsize, d0.winstep, d0.deltaws, d0.threshold,
-                                         d0.lambdac, d0.metric)
+        parts = [rec.chains(v) for rec, v in zip(self.recs, self.views)]
+        self.owner = np.cumsum([0] + [len(sa) for sa, _ in parts])
+        self.seg_a = np.concatenate([sa for sa, _ in parts]) if parts else np.zeros(0, dtype=np.int64)
+        self.seg_b = np.concatenate([sb for _, sb in parts]) if parts else np.zeros(0, dtype=np.int64)
+        d0 = pcd.Detector(self.rate, threshold=self.threshold, ctx=self.ctx, **D2_CHANGE)
+        self.win, self.first = self.pack.gw_run(self.seg_a, self.seg_b, d0.rate, d0.winsize, d0.winstep, d0.deltaws,
+                                                d0.threshold, d0.lambdac, d0.metric)
+        self.metric_cd = d0.metric
         return self
 
     def stage_b(self):
-        from . import clustering as pcl
-        self.seg_lines = []
-        self.seg_records = []
-        for r, (det, rec, v) in enumerate(zip(self.dets, self.parsed, self.views)):
-            win, first = self.gw[r]
-            c0 = 0
-            for feat, ch in self.groups[r]:                  # usually one group: one wav per recipe
-                lo, hi = int(first[c0]), int(first[c0 + len(ch)])
-                sub = win[lo:hi].copy()
-                sub['chain'] -= c0
-                det.prefetch(feat, ch, (sub, first[c0:c0 + len(ch) + 1] - first[c0]))
-                c0 += len(ch)
-            seg = io.StringIO()
-            det.writer.record = []
-            det.detect_changes(rec, seg, loader=lambda l, v=v: v)
-            self.seg_lines.append(seg.getvalue().splitlines(True))
-            self.seg_records.append(det.writer.record)
-        self.cls = [pcl.Clusterer(self.rate, variant=1, threshold=self.threshold, ctx=self.ctx, **D2_CLUSTER)
-                    for _ in self.batch]
-        # the clustering stage reads the segmentation RECIPE (text, times rounded to 12 digits): the same
-        # values without the regular-expression searches
-        self.seg_parsed = [recipe_mod.lines_from_records(recs, lines)
-                           for recs, lines in zip(self.seg_records, self.seg_lines)]
-        self.problems = [cl.initial_segments(rec, v.n)
-                         for cl, rec, v in zip(self.cls, self.seg_parsed, self.views)]
-        self.live = [r for r, p in enumerate(self.problems) if p]
+        import numpy as np
+        from . import _abi
+        parts = []
+        for r, rec in enumerate(self.recs):
+            first = self.first[self.owner[r]:self.owner[r + 1] + 1]
+            try:
+                parts.append(rec.segment(self.win, first, int(self.owner[r])))
+            except _abi.ReplayUnsupported:
+                parts.append(self._python_again(r).segment(self.win, first, int(self.owner[r])))
+        self.pfirst = np.cumsum([0] + [len(sa) for sa, _ in parts]).astype(np.int64)
+        self.turn_a = np.concatenate([sa for sa, _ in parts]) if parts else np.zeros(0, dtype=np.int64)
+        self.turn_b = np.concatenate([sb for _, sb in parts]) if parts else np.zeros(0, dtype=np.int64)
         return self
 
     def stage_c(self):
-        c0 = self.cls[0]
+        from . import _abi
+        metric, lam = _abi.METRIC[D2_CLUSTER['distance']], D2_CLUSTER['lambdac']
+        size = self.pfirst[1:] - self.pfirst[:-1]
         # The batched engine runs ONE CTA per recording and sizes its workspaces from the largest problem of
         # the batch (148 x nmax^2 doubles): recordings with many turns go through the resident engine (whole
         # GPU per recording) so that one long file neither starves nor overflows the batch.
-        small = [r for r in self.live if len(self.problems[r]) <= BATCH_MAX_SEGMENTS]
-        got = self.pack.cluster_batch([self.problems[r] for r in small], c0.metric, c0.lambdac,
-                                      self.threshold, 0, 1) if small else []
-        by_rec = dict(zip(small, got))
-        for r in self.live:
-            if r not in by_rec:
-                sa = [a for a, _ in self.problems[r]]
-                sb = [b for _, b in self.problems[r]]
-                with self.views[r].cluster(sa, sb, c0.metric, c0.lambdac) as cl:
-                    by_rec[r] = cl.run(self.threshold, 0, 1)
-        self.merged = [by_rec[r] for r in self.live]
+        small = [r for r in range(len(self.recs)) if 0 < size[r] <= BATCH_MAX_SEGMENTS]
+        self.merged = [None] * len(self.recs)
+        if small:
+            got = self.pack.cluster_batch_rows([(self.turn_a[self.pfirst[r]:self.pfirst[r + 1]],
+                                                 self.turn_b[self.pfirst[r]:self.pfirst[r + 1]]) for r in small],
+                                               metric, lam, self.threshold, 0, 1)
+            for r, g in zip(small, got):
+                self.merged[r] = g
+        for r in range(len(self.recs)):
+            if size[r] > BATCH_MAX_SEGMENTS:
+                with self.pack.cluster(self.turn_a[self.pfirst[r]:self.pfirst[r + 1]],
+                                       self.turn_b[self.pfirst[r]:self.pfirst[r + 1]], metric, lam) as cl:
+                    self.merged[r] = cl.run(self.threshold, 0, 1)
         return self
 
     def stage_d(self):
-        out = []
-        where = {r: k for k, r in enumerate(self.live)}
-        for r, (cl, rec, v) in enumerate(zip(self.cls, self.seg_parsed, self.views)):
-            if r in where:
-                cl.prefetch(v, self.problems[r], self.merged[where[r]])
-            clu = io.StringIO()
-            cl.process_recipe(rec, clu, loader=lambda l, v=v: v)
-            summary = dict(turns=len(self.seg_lines[r]), speakers=len(cl.speakers),
-                           windows=self.dets[r].windows_visited, merges=len(cl.merges))
-            out.append((''.join(self.seg_lines[r]), clu.getvalue(), summary))
-        return out
+        return [rec.finish(self.merged[r]) for r, rec in enumerate(self.recs)]
 
     def close(self):
+        for rec in self.recs:
+            rec.close()
         if self.pack is not None:
             self.pack.close()
             self.pack = None
 
 
-def diarize_batch(ctx, batch, frame_rate=125, threshold=0.0):
+def diarize_batch(ctx, batch, frame_rate=125, threshold=0.0, native=True):
     """A batch of recordings through change detection + clustering with the device work of the
     WHOLE batch in a handful of launches: packed upload + statistics, one growing-window launch over
     the chains of all recordings (one CTA per chain), one clustering launch (one CTA per recording).
     ``batch``: list of (recipe_lines, frames).  Returns [(segmentation recipe text, clustered
     recipe text, summary)] - byte-identical to ``diarize_recording`` on each item (the packed
     statistics restart per recording; the host replay is the same code)."""
-    job = _BatchJob(ctx, batch, frame_rate, threshold)
+    job = _BatchJob(ctx, batch, frame_rate, threshold, native)
     try:
         return job.stage_a().stage_b().stage_c().stage_d()
     finally:
         job.close()
 
 
-def diarize_batches(ctx, batches, frame_rate=125, threshold=0.0):
-    """``diarize_batch`` over a sequence of batches with the stages OVERLAPPED: a worker thread
-    queues the device stages (the context's calls are serialised; ctypes releases the GIL inside
-    them) while this thread replays records.  While the host replays batch k, the device already
-    uploads batch k + 1 and searches it; the clustering launch of batch k queues behind.  Up to
-    three packed batches are resident at a time (6,560 B per frame each).  Yields the result list
-    of every batch, in order; results are those of ``diarize_batch``."""
+def diarize_batches(ctx, batches, frame_rate=125, threshold=0.0, native=True, lanes=2):
+    """``diarize_batch`` over a sequence of batches in ``lanes`` LANES that overlap each other:
+    every lane is a thread with its own context (its own stream) on the same device and takes
+    batches k, k + lanes, ... through the four stages one after the other (every ABI call is
+    synchronous and releases the GIL).  While the growing-window search of one batch occupies the
+    SMs, the next batch's frames cross PCIe on the other lane's stream (26 of the 88 ms a batch of
+    148 ten-minute recordings needs on the device are that copy), and the short host stages
+    (native replay) of one lane hide behind device work of the other.  Lane 0 uses ``ctx``; the
+    others use contexts that ``ctx`` keeps for this purpose (``Context.lane_contexts``).  One packed batch per lane is resident
+    (6,560 B per frame).  Yields the result list of every batch, in order; results are those of
+    ``diarize_batch``."""
     from concurrent.futures import ThreadPoolExecutor
     batches = list(batches)
     if not batches:
         return
-    with ThreadPoolExecutor(max_workers=1) as dev:
-        jobs = [_BatchJob(ctx, b, frame_rate, threshold) for b in batches]
-        try:
-            fa = dev.submit(jobs[0].stage_a)
-            prev = None                                         # (job, future of its stage C)
-            for k, job in enumerate(jobs):
-                fa.result()
-                if k + 1 < len(jobs):
-                    fa = dev.submit(jobs[k + 1].stage_a)        # device: upload + search of the next batch ...
-                job.stage_b()                                   # ... while the host replays this one
-                fc = dev.submit(job.stage_c)
-                if prev is not None:
-                    prev[1].result()
-                    out = prev[0].stage_d()
-                    dev.submit(prev[0].close)
-                    yield out
-                prev = (job, fc)
-            prev[1].result()
-            out = prev[0].stage_d()
-            dev.submit(prev[0].close).result()
-            yield out
-        finally:
-            for job in jobs:
-                try:
-                    dev.submit(job.close).result()
-                except Exception:           # pragma: no cover - the first error is the one to report
-                    pass
+    lanes = max(1, min(int(lanes), len(batches)))
+    pools = []
+    try:
+        ctxs = [ctx] + ctx.lane_contexts(lanes - 1)
+        pools = [ThreadPoolExecutor(max_workers=1) for _ in range(lanes)]
+
+        def run(k):
+            job = _BatchJob(ctxs[k % lanes], batches[k], frame_rate, threshold, native)
+            try:
+                return job.stage_a().stage_b().stage_c().stage_d()
+            finally:
+                job.close()
+        # a lane holds at most one finished batch ahead of the consumer
+        futs = {}
+        nxt = 0
+        for k in range(len(batches)):
+            while nxt < len(batches) and nxt < k + 2 * lanes:
+                futs[nxt] = pools[nxt % lanes].submit(run, nxt)
+                nxt += 1
+            yield futs.pop(k).result()
+    finally:
+        for pool in pools:
+            pool.shutdown(wait=True, cancel_futures=True)
 
 
 def run_corpus(items, rank=0, world=1, device=None, outdir=None, frame_rate=125, runner=None,

@@ -80,6 +80,22 @@ __device__ __forceinline__ void cl_track(double d, unsigned long long* stat) {  
     atomicMax(stat + 0, cl_ord(d));
     atomicMin(stat + 1, cl_ord(d));
 }
+// The same statistics kept in registers while a warp works through its pairs and folded into the two global
+// words ONCE at the end: every pair sending two atomics to the same two addresses (2 x 12,000 per merge at
+// 24,000 clusters, 2 x 1.96 M in the fill of config 3) queues them up in one L2 slice.  Maximum and minimum
+// of ordered keys do not depend on the order, so the result is the same to the bit.
+struct ClTrack {
+    unsigned long long hi = 0ULL, lo = ~0ULL;               // ordered keys; (0, ~0) = nothing seen
+    __device__ __forceinline__ void see(double d) {
+        if (d == d_inf() || d == -d_inf() || d != d) return;
+        const unsigned long long k = cl_ord(d);
+        hi = k > hi ? k : hi;
+        lo = k < lo ? k : lo;
+    }
+    __device__ __forceinline__ void flush(unsigned long long* stat) const {
+        if (hi >= lo) { atomicMax(stat + 0, hi); atomicMin(stat + 1, lo); }
+    }
+};
 
 static __global__ void __launch_bounds__(256)
 cl_init_records(const Stats st, const int64_t* __restrict__ seg, int64_t n,
@@ -140,16 +156,34 @@ cl_fill_pairs(const double* rec, const double* __restrict__ ld, int64_t n, int m
     WarpScratch* ws = reinterpret_cast<WarpScratch*>(sc_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t npair = (n * (n - 1)) / 2;
-    for (int64_t p = (int64_t)blockIdx.x * SC_WARPS + warp; p < npair; p += (int64_t)gridDim.x * SC_WARPS) {
-        int64_t i, j;
-        cl_pair(p, n, i, j);
-        const RecSrc X{rec + i * REC}, Y{rec + j * REC};
-        const double d = cl_pair_distance(metric, lambda, X, Y, ld[i], ld[j], ws[warp], lane);
+    // every warp takes a CONTIGUOUS run of pairs (row-major over the upper triangle): the record of cluster i
+    // stays staged in shared memory while the run stays in row i - one record load per pair instead of two
+    const int64_t gw = (int64_t)blockIdx.x * SC_WARPS + warp, nw = (int64_t)gridDim.x * SC_WARPS;
+    const int64_t per = (npair + nw - 1) / nw;
+    int64_t p = gw * per;
+    const int64_t pe = p + per < npair ? p + per : npair;
+    if (p >= pe) return;
+    WarpScratch& w = ws[warp];
+    int64_t i, j, staged = -1;
+    cl_pair(p, n, i, j);
+    ClTrack track;
+    for (; p < pe; ++p) {
+        if (i != staged) {
+            __syncwarp();
+            stage_record(RecSrc{rec + i * REC}, w.rec[0], lane);
+            __syncwarp();
+            staged = i;
+        }
+        const SmemSrc X{w.rec[0]};
+        const RecSrc Y{rec + j * REC};
+        const double d = cl_pair_distance(metric, lambda, X, Y, ld[i], ld[j], w, lane);
         if (lane == 0) {
             M[i * n + j] = d;
-            if (variant == 1) { M[j * n + i] = d; cl_track(d, stat); }
+            if (variant == 1) { M[j * n + i] = d; track.see(d); }
         }
+        if (++j == n) { ++i; j = i + 1; }
     }
+    if (lane == 0) track.flush(stat);
 }
 
 // One mailbox slot per (parity, sending rank): the sender writes the payload, then the sequence
@@ -335,9 +369,20 @@ __device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, i
     // gets two pairs while another has none because of where the dead indices happen to lie).
     // select(o) = index of the o-th alive cluster: lanes count the bits of their share of the
     // mask words, a warp scan finds the lane that holds the target, that lane walks its words.
+    // Sharded run: this rank scores the pairs (a, k) with (a + k) % nranks == rank, i.e. the clusters k of ONE
+    // residue class - the ordinals count only those (for a power-of-two number of ranks the class is the same bit
+    // pattern in every mask word), so that a rank's share of the row is dealt densely over its warps too.  Other
+    // rank counts keep the dense numbering of all alive clusters and skip the pairs of the other ranks.
+    const bool by_class = g.nranks > 1 && g.nranks <= 32 && (g.nranks & (g.nranks - 1)) == 0;
+    uint32_t cls = 0xffffffffu;
+    if (by_class) {
+        const int c0 = (int)(((int64_t)g.rank - a % g.nranks + g.nranks) % g.nranks);
+        cls = 0;
+        for (int bit = c0; bit < 32; bit += g.nranks) cls |= 1u << bit;
+    }
     const int wpl = (nwords + 31) / 32;                       // mask words per lane
     int mycnt = 0;
-    for (int w = lane * wpl; w < (lane + 1) * wpl && w < nwords; ++w) mycnt += __popc(abits[w]);
+    for (int w = lane * wpl; w < (lane + 1) * wpl && w < nwords; ++w) mycnt += __popc(abits[w] & cls);
     int incl = mycnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -353,7 +398,7 @@ __device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, i
         if (mine) {
             int rem = (int)o - excl;
             for (int w = lane * wpl;; ++w) {
-                const uint32_t word = abits[w];
+                const uint32_t word = abits[w] & cls;
                 const int c = __popc(word);
                 if (rem < c) { found = (int64_t)w * 32 + (__fns(word, 0, rem + 1)); break; }
                 rem -= c;
@@ -373,6 +418,7 @@ __device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, i
     const double N1 = sm.merged[L39::CNT];
     double ld_ab = 0.0;
     ClBest rowa{d_inf(), INT64_MAX};             // lane 0: best (distance, k) this warp produced for row a
+    ClTrack track;                               // lane 0: extremes of the distances this warp computed
     for (int round = 0;; ++round) {
         bool has; int term; int64_t kk;
         if (round == 0 && warp == ldw && !sm.wbusy[ldw]) { has = true; term = 0; kk = a; }       // a spare warp
@@ -380,6 +426,15 @@ __device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, i
         else { has = mine_pair(k); term = 2; kk = has ? k : a; }
         if (round > 0 && k >= n) break;
         double t = 0.0;
+        // what lane 0 needs next to ln|S_pooled|: asked for BEFORE the factorisation, which hides the round trips
+        double N2 = 0.0, ldk = 0.0, vold = 0.0;
+        int32_t cmin = -1;
+        if (has && term == 2 && lane == 0) {
+            N2 = __ldcg(g.rec + kk * REC + L39::CNT);
+            ldk = __ldcg(g.ld + kk);
+            cmin = __ldcg(g.rowmin_c + kk);
+            if (g.variant == 1) vold = __ldcg(g.rowmin_v + kk);
+        }
         if (has) {
             const RecSrc Y{g.rec + kk * REC};
             t = logdet_term(term, g.metric, X, Y, sm.ws[warp], lane);
@@ -390,17 +445,13 @@ __device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, i
             ld_ab = sm.shd[0];
         }
         if (has && term == 2 && lane == 0) {
-            const double N2 = __ldcg(g.rec + kk * REC + L39::CNT);
-            const double ldk = __ldcg(g.ld + kk);
             const double d = g.metric == SPKDIAR_BIC ? bic_combine(N1, N2, ld_ab, ldk, t, g.lambda)
                                                      : glr_combine(N1, N2, ld_ab, ldk, t);
             g.M[a * n + kk] = d;                                            // row a
             cl_take(rowa, d, kk);                                            // minimum of the new row a
-            const int32_t cmin = __ldcg(g.rowmin_c + kk);
             bool flag = false;
             if (g.variant == 1) {
-                g.M[kk * n + a] = d; cl_track(d, g.stat);                   // and column a
-                const double vold = __ldcg(g.rowmin_v + kk);
+                g.M[kk * n + a] = d; track.see(d);                          // and column a
                 if (cmin == (int32_t)b) flag = true;
                 else if (cmin == (int32_t)a) {
                     // the row's minimum sat in the rewritten column: it stays there unless it got worse
@@ -418,6 +469,7 @@ __device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, i
         ord += nwarps;
         k = select(ord);
     }
+    if (lane == 0) track.flush(g.stat);
     // A row whose pair with a belongs to ANOTHER rank still loses column b here: if its cached
     // minimum sat there (or in the column a another rank rewrites - not this rank's entry, so the
     // local row only loses it) it has to be rescanned.  One lane per row.
@@ -731,6 +783,7 @@ cl_fill_pairs_shard(const double* rec, const double* __restrict__ ld, int64_t n,
     // cyclically, a row's owned pairs in turn
     const int64_t gw = (int64_t)blockIdx.x * SC_WARPS + warp, nw = (int64_t)gridDim.x * SC_WARPS;
     // linear index over (i, t): row i has cnt(i) = number of j > i with (i + j) % nranks == rank
+    ClTrack track;
     for (int64_t i = 0; i < n - 1; ++i) {
         int64_t j0 = i + 1 + ((((int64_t)rank - 2 * i - 1) % nranks) + nranks) % nranks;
         // warps stride over the owned pairs of the row, offset by the row so that short rows do not
@@ -739,9 +792,10 @@ cl_fill_pairs_shard(const double* rec, const double* __restrict__ ld, int64_t n,
             const int64_t j = j0 + t * nranks;
             const RecSrc X{rec + i * REC}, Y{rec + j * REC};
             const double d = cl_pair_distance(metric, lambda, X, Y, ld[i], ld[j], ws[warp], lane);
-            if (lane == 0) { M[i * n + j] = d; M[j * n + i] = d; cl_track(d, stat); }
+            if (lane == 0) { M[i * n + j] = d; M[j * n + i] = d; track.see(d); }
         }
     }
+    if (lane == 0) track.flush(stat);
 }
 
 // spk-clustering2.py:220: distances.max() over the compacted matrix (NaN propagates)

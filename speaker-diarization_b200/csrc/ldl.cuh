@@ -6,7 +6,7 @@
 // sufficient-statistics records, factorised as L diag(p) L^T without square
 // roots, and  ln|S| = sum ln p_c - D ln(n-1).
 //
-// Register layout: see layout.cuh (block-cyclic 4 x 8 lane grid, 30 slots per
+// Register layout: see layout.cuh (block-cyclic 8 x 4 lane grid, 30 slots per
 // lane).  The factorisation is right-looking: at step c the owners of column c
 // publish it to a 2x40-double shared-memory strip, one __syncwarp later all lanes
 // read the pivot and the entries they need back and apply the rank-1 update to
@@ -127,7 +127,7 @@ __device__ __forceinline__ const double* stage_record(const SmemSrc& src, double
 //   FORM_POOL  M = (Qx+Qy) - (sx+sy)(sx+sy)^T / (nx+ny)      (BIC pooled term)
 //   FORM_MIX   M = wx (Qx - sx sx^T/nx) + wy (Qy - sy sy^T/ny)   (GLR, CD:114-115)
 //
-// Lane (i, j) = (lane / 8, lane % 8) fills its slots (kj, ri) <-> entry (i + 4 ri, j + 8 kj),
+// Lane (i, j) = (lane / PC, lane % PC) fills its slots (kj, ri) <-> entry (i + PR ri, j + PC kj),
 // see layout.cuh.  Returns the frame count the matrix stands for (nx, ny, nx+ny; 0 for MIX).
 enum { FORM_X = 0, FORM_Y = 1, FORM_POOL = 2, FORM_MIX = 3 };
 
@@ -150,7 +150,7 @@ __device__ __forceinline__ double form_matrix(double (&a)[Grid<D>::NSLOT],
     double ax = ux ? 1.0 : 0.0, ay = uy ? 1.0 : 0.0, c1, c2 = 0.0;
     if (two) { ax = wx; ay = wy; c1 = wx / nx; c2 = wy / ny; }
     else c1 = 1.0 / (nx + ny);
-    const int i = lane >> 3, j = lane & 7;
+    const int i = G::lane_i(lane), j = G::lane_j(lane);
     double u1[G::NRI], u2[G::NRI];
 #pragma unroll
     for (int ri = 0; ri < G::NRI; ++ri) {
@@ -179,8 +179,6 @@ __device__ __forceinline__ double form_matrix(double (&a)[Grid<D>::NSLOT],
 
 // ---- factorisation ---------------------------------------------------------------
 // Returns ln|M| (sum of the logs of the D pivots), NaN when a pivot is not > 0.
-// STORE: also leave the strict lower triangle of L (row-major, row r at
-// r(r-1)/2) in Lsm and the reciprocal pivots in pinv (both shared memory).
 // One elimination step, column C known at compile time (template recursion: nvcc does
 // not fully unroll a 39-trip loop with this much body, and a rolled loop would index
 // the register array dynamically, i.e. push it to local memory):
@@ -207,110 +205,91 @@ __device__ __forceinline__ double fast_rcp(double a) {
     return fma(y, f, y);
 }
 
+// does lane row-group i of local row ri hold a row r = i + PR ri with C < r < D?  After unrolling, ri and C
+// are constants: only the boundary group (rows around C) and the last group (rows around D) test anything
+template <int D>
+__device__ __forceinline__ bool live_row(bool p, int i, int ri, int C) {
+    using G = Grid<D>;
+    const int lo = G::PR * ri;
+    if (lo <= C) p = p && (i > C - lo);
+    if (lo + G::PR - 1 >= D) p = p && (i < D - lo);
+    return p;
+}
+
 // One elimination step.  On entry the lane already holds what it needs of column C
 // (read from the strip by the previous step): the pivot, the entries vr[] of its own
-// rows and vk[] of its own columns, q = 1 / pivot - and, for the LOOK-AHEAD, vnx = M(C+1, C)
-// and dn = the diagonal entry (C+1, C+1) as it stands before this step.  With those every lane
-// computes the NEXT pivot itself, npiv = dn - (vnx q) vnx (the very fma the owner of that entry
-// executes: same bits), and starts its reciprocal at once; the dependent chain of a step is then
-// q -> multiply -> fma -> reciprocal (about 63 cycles) next to, not behind, the strip round trip
-// multiply -> fma -> store -> __syncwarp -> load (about 55).  The step
-// (1) updates column C + 1 and the diagonal entry (C+2, C+2) and publishes them (the diagonal in
-//     strip slot VS - 1), (2) reads its part of column C + 1 back, (3) applies the rest of the
-// rank-1 update.
-// (Measured on B200, one warp alone, before the look-ahead: 195 cycles per step, of which about
-// 105 were the chain strip round trip -> reciprocal -> multiply -> FMA; a variant that takes the
-// next pivot by warp shuffle was slower.)
-template <int D, bool STORE, int C>
+// rows and vk[] of its own columns, and q = 1 / pivot is on its way.  The step
+// (1) updates column C + 1 and publishes it, (2) reads its part of column C + 1 back
+// and starts the next reciprocal, (3) applies the rest of the rank-1 update.
+// Measured on B200: one warp alone is a latency chain (strip round trip -> reciprocal ->
+// multiply -> FMA per step); twelve warps on an SM are bound by the shared-memory pipe -
+// 2 cycles per store instruction + 1 per load accounted for 11.9 k of the 12.3 k cycles of
+// the 4 x 8 layout - hence the layout with the fewest stores (layout.cuh) and no traffic
+// beyond the column itself (a look-ahead of the next pivot through an extra strip slot
+// saved 9 % alone and cost 4 pipe cycles per step under load: removed).
+template <int D, int C>
 struct LdlStep {
     using G = Grid<D>;
     static __device__ __forceinline__ void run(double (&a)[G::NSLOT], LdlScratch& w, int lane, int i, int j,
                                                const double (&vr)[G::NRI], const double (&vk)[G::NKJ],
-                                               double piv, double q, double vnx, double dn,
-                                               double& p0, double& p1, bool& bad, double* Lsm, double* pinv) {
+                                               double piv, double q, double& p0, double& p1) {
         constexpr int ri_a = (C + 1) / G::PR;          // first local row that can hold a row > C
         constexpr int kj_a = (C + 1) / G::PC;          // first local column that can hold a column > C
         constexpr int kn = (C + 1) / G::PC, jn = (C + 1) % G::PC;     // local column / owner lanes of column C + 1
-        // the diagonal entry (C+2, C+2): local column / row and owner lane
-        constexpr int k2 = (C + 2) / G::PC, j2 = (C + 2) % G::PC, r2 = (C + 2) / G::PR, i2 = (C + 2) % G::PR;
-        constexpr bool ahead = C + 2 < D;
-        constexpr bool extra = ahead && k2 != kn;      // it does not lie in the local column updated first
         double* vn = w.v[(C + 1) & 1];
-        bad |= !(piv > 0.0);
         if ((C & 31) == lane) { if (C < 32) p0 = piv; else p1 = piv; }
-        // look-ahead: the next pivot and its reciprocal, from values every lane holds
-        double npiv = 1.0, nq = 1.0;
-        if (C + 1 < D) {
-            npiv = fma(-(vnx * q), vnx, dn);
-            nq = fast_rcp(npiv);
-        }
         double lr[G::NRI];
 #pragma unroll
         for (int ri = ri_a; ri < G::NRI; ++ri) lr[ri] = vr[ri] * q;
-        double nvr[G::NRI], nvk[G::NKJ], nvnx = 0.0, ndn = 1.0;
+        double nvr[G::NRI], nvk[G::NKJ], npiv = 1.0, nq = 1.0;
         if (C + 1 < D) {
-            // (1) column C + 1 first (and the diagonal after it): update and hand over at once
+            // (1) column C + 1 first: update it and hand it over at once
+            const bool pj = j == jn;
 #pragma unroll
             for (int ri = (ri_a > G::ri_first(kn) ? ri_a : G::ri_first(kn)); ri < G::NRI; ++ri) {
-                const int r = i + G::PR * ri;
                 const double m = fma(-lr[ri], vk[kn], a[G::slot(kn, ri)]);
                 a[G::slot(kn, ri)] = m;
-                st_shared_if(j == jn && r > C && r < D, vn + r, m);
+                st_shared_if(live_row<D>(pj, i, ri, C), vn + i + G::PR * ri, m);
             }
-            if (extra) a[G::slot(k2, r2)] = fma(-lr[r2], vk[k2], a[G::slot(k2, r2)]);
-            if (ahead) st_shared_if(i == i2 && j == j2, vn + (VS - 1), a[G::slot(k2, r2)]);
             __syncwarp();
             // (2) what the next step needs of column C + 1
             constexpr int ri_n = (C + 2) / G::PR, kj_n = (C + 2) / G::PC;
+            npiv = vn[C + 1];
 #pragma unroll
             for (int ri = ri_n; ri < G::NRI; ++ri) nvr[ri] = vn[i + G::PR * ri];
 #pragma unroll
             for (int kj = kj_n; kj < G::NKJ; ++kj) nvk[kj] = vn[j + G::PC * kj];
-            if (ahead) { nvnx = vn[C + 2]; ndn = vn[VS - 1]; }
+            nq = fast_rcp(npiv);
             // (3) the rest of the update of step C
 #pragma unroll
             for (int kj = kj_a; kj < G::NKJ; ++kj) {
                 if (kj == kn) continue;
 #pragma unroll
-                for (int ri = (ri_a > G::ri_first(kj) ? ri_a : G::ri_first(kj)); ri < G::NRI; ++ri) {
-                    if (extra && kj == k2 && ri == r2) continue;        // done in (1)
+                for (int ri = (ri_a > G::ri_first(kj) ? ri_a : G::ri_first(kj)); ri < G::NRI; ++ri)
                     a[G::slot(kj, ri)] = fma(-lr[ri], vk[kj], a[G::slot(kj, ri)]);
-                }
             }
         }
-        if (STORE) {
-            constexpr int jC = C % G::PC;
-#pragma unroll
-            for (int ri = ri_a; ri < G::NRI; ++ri) {
-                const int r = i + G::PR * ri;
-                st_shared_if(j == jC && r > C && r < D, Lsm + (r * (r - 1)) / 2 + C, lr[ri]);
-            }
-            st_shared_if(lane == 0, pinv + C, q);
-        }
-        LdlStep<D, STORE, C + 1>::run(a, w, lane, i, j, nvr, nvk, npiv, nq, nvnx, ndn, p0, p1, bad, Lsm, pinv);
+        LdlStep<D, C + 1>::run(a, w, lane, i, j, nvr, nvk, npiv, nq, p0, p1);
     }
 };
-template <int D, bool STORE>
-struct LdlStep<D, STORE, D> {
+template <int D>
+struct LdlStep<D, D> {
     using G = Grid<D>;
     static __device__ __forceinline__ void run(double (&)[G::NSLOT], LdlScratch&, int, int, int,
                                                const double (&)[G::NRI], const double (&)[G::NKJ], double, double,
-                                               double, double, double&, double&, bool&, double*, double*) {}
+                                               double&, double&) {}
 };
 
-template <int D, bool STORE>
-__device__ __forceinline__ double ldl_logdet(double (&a)[Grid<D>::NSLOT], LdlScratch& w, int lane,
-                                             double* Lsm = nullptr, double* pinv = nullptr) {
+template <int D>
+__device__ __forceinline__ double ldl_logdet(double (&a)[Grid<D>::NSLOT], LdlScratch& w, int lane) {
     using G = Grid<D>;
-    static_assert(VS - 1 >= D, "the strip needs a spare slot for the look-ahead diagonal");
+    static_assert(D <= 64 && G::PR * G::NRI <= VS && G::PC * G::NKJ <= VS, "pivots in two registers per lane, strip covers the grid");
     double p0 = 1.0, p1 = 1.0;             // pivots c == lane and c == lane + 32
-    bool bad = false;
-    const int i = lane >> 3, j = lane & 7;
+    const int i = G::lane_i(lane), j = G::lane_j(lane);
     __syncwarp();                          // the strips may still be read by a slower lane of the previous task
 #pragma unroll
-    for (int ri = 0; ri < G::NRI; ++ri)    // prologue: publish column 0 (and the diagonal entry (1, 1)), read back
-        st_shared_if(j == 0 && i + G::PR * ri < D, w.v[0] + i + G::PR * ri, a[G::slot(0, ri)]);
-    if (D > 1) st_shared_if(i == 1 % G::PR && j == 1 % G::PC, w.v[0] + (VS - 1), a[G::slot(1 / G::PC, 1 / G::PR)]);
+    for (int ri = 0; ri < G::NRI; ++ri)    // prologue: publish column 0 and read it back
+        st_shared_if(live_row<D>(j == 0, i, ri, -1), w.v[0] + i + G::PR * ri, a[G::slot(0, ri)]);
     __syncwarp();
     double vr[G::NRI], vk[G::NKJ];
     const double piv = w.v[0][0];
@@ -318,12 +297,13 @@ __device__ __forceinline__ double ldl_logdet(double (&a)[Grid<D>::NSLOT], LdlScr
     for (int ri = 0; ri < G::NRI; ++ri) vr[ri] = w.v[0][i + G::PR * ri];
 #pragma unroll
     for (int kj = 0; kj < G::NKJ; ++kj) vk[kj] = w.v[0][j + G::PC * kj];
-    const double vnx = D > 1 ? w.v[0][1] : 0.0, dn = D > 1 ? w.v[0][VS - 1] : 1.0;
-    LdlStep<D, STORE, 0>::run(a, w, lane, i, j, vr, vk, piv, fast_rcp(piv), vnx, dn, p0, p1, bad, Lsm, pinv);
+    LdlStep<D, 0>::run(a, w, lane, i, j, vr, vk, piv, fast_rcp(piv), p0, p1);
     double s = log(p0);
     if (D > 32) s += log(p1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    // NaN when a pivot is not > 0 (a log alone would let a last pivot of exactly 0 through as -inf)
+    const bool bad = __any_sync(0xffffffffu, !(p0 > 0.0) || !(p1 > 0.0));
     __syncwarp();
     return bad ? __longlong_as_double(0x7ff8000000000000LL) : s;
 }
@@ -361,7 +341,7 @@ struct LdlInvStep {
             const double l = vr[ri] * q;
             lr[ri] = (ri > rib || i > iC) ? l : 0.0;
         }
-        // one update per slot (kj, ri), ri >= max(2 kj, rib):
+        // one update per slot (kj, ri), ri >= max(ri_first(kj), rib):
         //   k > C : M_rk -= l_rC M_kC       k < C : X_rk -= l_rC X_Ck       k == C : X_rC = -l_rC
         auto update = [&](int kj, int ri) {
             const int sl = G::slot(kj, ri);
@@ -379,10 +359,8 @@ struct LdlInvStep {
             for (int kj = 0; kj < G::NKJ; ++kj)
                 if (kj != kn && rn >= G::ri_first(kj) && rn >= rib) update(kj, rn);
 #pragma unroll
-            for (int ri = (rib > G::ri_first(kn) ? rib : G::ri_first(kn)); ri < G::NRI; ++ri) {
-                const int r = i + G::PR * ri;
-                st_shared_if(j == jn && r > C && r < D, vn + r, a[G::slot(kn, ri)]);
-            }
+            for (int ri = (rib > G::ri_first(kn) ? rib : G::ri_first(kn)); ri < G::NRI; ++ri)
+                st_shared_if(live_row<D>(j == jn, i, ri, C), vn + i + G::PR * ri, a[G::slot(kn, ri)]);
 #pragma unroll
             for (int kj = 0; kj <= kn; ++kj) {
                 if (rn < G::ri_first(kj)) continue;
@@ -430,11 +408,11 @@ __device__ __forceinline__ double ldl_logdet_inv(double (&a)[Grid<D>::NSLOT], Ld
     using G = Grid<D>;
     double p0 = 1.0, p1 = 1.0;
     bool bad = false;
-    const int i = lane >> 3, j = lane & 7;
+    const int i = G::lane_i(lane), j = G::lane_j(lane);
     __syncwarp();
 #pragma unroll
     for (int ri = 0; ri < G::NRI; ++ri)    // prologue: publish column 0 and read it back (row 0 of X is empty)
-        st_shared_if(j == 0 && i + G::PR * ri < D, w.v[0] + i + G::PR * ri, a[G::slot(0, ri)]);
+        st_shared_if(live_row<D>(j == 0, i, ri, -1), w.v[0] + i + G::PR * ri, a[G::slot(0, ri)]);
     __syncwarp();
     double vr[G::NRI], cf[G::NKJ];
     const double piv = w.v[0][0];
@@ -462,8 +440,8 @@ __device__ __forceinline__ double ldl_logdet_inv(double (&a)[Grid<D>::NSLOT], Ld
             const double x = (r > k && r < D) ? a[G::slot(kj, ri)] : 0.0;
             acc = fma(x * x, qr[ri], acc);
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+#pragma unroll
+        for (int o = G::PC; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);      // over the PR lanes of a column
         if (i == 0 && k < D) dinv[k] = bad ? __longlong_as_double(0x7ff8000000000000LL) : (acc + pinv[k]) * scale;
     }
     __syncwarp();

@@ -82,7 +82,7 @@ __device__ __forceinline__ double logdet_term(int term, int metric, const SrcX& 
     double wx = 1.0, wy = 1.0;
     if (kind == FORM_MIX) glr_weights(sx(L39::CNT), sy(L39::CNT), wx, wy);
     const double n = form_matrix<D39>(a, kind, sx, sy, wx, wy, w, lane);
-    const double lm = ldl_logdet<D39, false>(a, w, lane);
+    const double lm = ldl_logdet<D39>(a, w, lane);
     if (kind == FORM_MIX) return range_map(lm);
     return finish_logdet(lm, n, D39);
 }

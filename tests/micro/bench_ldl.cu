@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(384, 1) k(const double* rec, int ntask, double
         const SmemSrc sx{rx};
         const double n = form_matrix<D39>(a, FORM_X, sx, sx, 1.0, 1.0, w, lane);
         const long long c2 = clock64();
-        const double lm = ldl_logdet<D39, false>(a, w, lane);
+        const double lm = ldl_logdet<D39>(a, w, lane);
         const long long c3 = clock64();
         const double v = finish_logdet(lm, n, D39);
         if (lane == 0) out[warp * ntask + it] = v;
