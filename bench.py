@@ -446,25 +446,37 @@ def run_other_workload(args):
         dist.destroy_process_group()
 
 
-C4_FILES = 296                  # the FIXED corpus of the config4 sub-record: recordings 0..295 of synth.config4_file
-C4_BATCH = 74
+C4_FILES = 1000                 # the FIXED corpus of the config4 sub-record: BASELINE config 4, recordings 0..999 of synth.config4_file
+C4_BATCH = 148                  # recordings per device batch (one CTA per recording in the growing-window launch)
 C5_SEGMENTS = 23940             # the FIXED long recording of the config5 sub-record (BASELINE config 5 scaled by 1/2)
 
 
 def sub_config4(ctx, rank, world, timed, steps=2):
-    """BASELINE config 4 as it shards: a FIXED corpus of ten-minute recordings, dealt to the ranks by file index
-    (recording k -> rank k % N, spk-diarization2.py:122-128 once per file, no communication), through the drop-in
-    corpus driver with HOST buffers: pinned frames in, recipe text out, device batches overlapped with the host
-    replay.  Strong scaling: the corpus does not grow with N."""
+    """BASELINE config 4 as it shards: a FIXED corpus of 1,000 ten-minute recordings, dealt to the ranks by file
+    index (recording k -> rank k % N, spk-diarization2.py:122-128 once per file, no communication), through the
+    drop-in corpus driver with HOST buffers: pinned frames in, recipe text out, device batches in two lanes that
+    overlap each other (copies of one batch under the kernels of the other), host replay in native code.
+    Strong scaling: the corpus does not grow with N."""
+    import multiprocessing as mp
     import torch
     from spkdiar import corpus, synth
     mine = corpus.shard(C4_FILES, rank, world)
+    # the synthetic recordings are generated on the host cores this rank may use (0.2 s each on one core)
+    workers = max(1, min(12, (os.cpu_count() or 1) // max(world, 1)))
+    if workers > 1 and len(mine) > 8:
+        with mp.get_context('spawn').Pool(workers) as pool:
+            frames = pool.map(synth.config4_frames, mine, chunksize=4)
+    else:
+        frames = [synth.config4_frames(k) for k in mine]
     items = []
-    for k in mine:
-        r = synth.config4_file(k)
-        items.append((synth.one_line_recipe('/syn/c4_%d.wav' % k, r), torch.from_numpy(r.frames).pin_memory()))
-    parts = [[(lines, (t.data_ptr(), t.shape[0])) for lines, t in items[b0:b0 + C4_BATCH]]
-             for b0 in range(0, len(items), C4_BATCH)]
+    for k, x in zip(mine, frames):
+        lines = ['audio=/syn/c4_%d.wav lna=a_1 start-time=0.0 end-time=%s\n' % (k, repr(x.shape[0] / float(RATE)))]
+        items.append((lines, torch.from_numpy(x).pin_memory()))
+    del frames
+    # two lanes: at least two batches per rank whenever there is more than one recording
+    batch = max(1, min(C4_BATCH, (len(items) + 1) // 2))
+    parts = [[(lines, (t.data_ptr(), t.shape[0])) for lines, t in items[b0:b0 + batch]]
+             for b0 in range(0, len(items), batch)]
 
     def step():
         out = None
@@ -474,9 +486,10 @@ def sub_config4(ctx, rank, world, timed, steps=2):
     step()
     ms, last = timed(step, steps)
     hours = C4_FILES * (60000 / RATE / 3600.0)
-    return {'what': 'FIXED corpus of %d ten-minute recordings, recording k on rank k %% N, gw BIC change detection + CL1 '
-                    'clustering (spk-diarization2.py flags) through corpus.diarize_batches: pinned host frames in, recipe '
-                    'text out, device batches of <= %d recordings overlapped with the host replay' % (C4_FILES, C4_BATCH),
+    return {'what': 'FIXED corpus of %d ten-minute recordings (BASELINE config 4), recording k on rank k %% N, gw BIC change '
+                    'detection + CL1 clustering (spk-diarization2.py flags) through corpus.diarize_batches: pinned host '
+                    'frames in, recipe text out, device batches of <= %d recordings in two overlapping lanes, host replay '
+                    'in native code (spkdiar_replay_*)' % (C4_FILES, batch),
             'scaling': 'strong', 'recordings': C4_FILES, 'recordings_this_rank': len(mine), 'steps': steps,
             'ms_per_step': ms / steps, 'value': steps * hours / (ms / 1e3), 'unit': 'audio-hours/s',
             'h2d_bytes_per_step': C4_FILES * 60000 * 39 * 4,

@@ -124,6 +124,12 @@ def config4_file(index, n_frames=60000):
     return make_recording(seed, n_frames, int(k))
 
 
+def config4_frames(index):
+    """Frames of ``config4_file(index)`` alone (a picklable job for a process pool: the benchmark
+    generates the 1,000 recordings on all host cores)."""
+    return config4_file(index).frames
+
+
 def config5(n_frames=8640000, seed=1005):
     """24 h, K = 20, ~50,000 segments of 100..246 frames."""
     return make_recording(seed, n_frames, 20, turn_lo=100, turn_hi=246, unit=1)
