@@ -362,7 +362,7 @@ def run_other_workload(args):
     if args.workload == 'config3':
         rec = synth.make_recording(1003 + rank, 1080000, 10, turn_lo=2, turn_hi=9)
         sa, sb = [t[0] for t in rec.turns], [t[1] for t in rec.turns]
-        feat = ctx.upload(rec.frames)
+        feat = ctx.upload_frames(rec.frames)         # clustering only: no window statistics (K5 records from the frames)
         hours_per_step, scaling = world * 3.0, 'weak'
         desc = 'config3: CL1 agglomerative BIC clustering of a 3-hour recording (%d segments) per GPU' % len(sa)
 
@@ -372,7 +372,7 @@ def run_other_workload(args):
     elif args.workload == 'config5':
         rec = synth.config5(n_frames=args.segments * 173)
         sa, sb = [t[0] for t in rec.turns], [t[1] for t in rec.turns]
-        feat = ctx.upload(rec.frames)
+        feat = ctx.upload_frames(rec.frames)         # clustering only: no window statistics (K5 records from the frames)
         mbx = sharded.Mailboxes(ctx) if world > 1 else None
         hours_per_step, scaling = rec.frames.shape[0] / RATE / 3600.0, 'strong'
         desc = ('config5 (scaled): one %.1f-hour recording, %d segments, pair matrix dealt over %d GPU(s), one '
@@ -505,7 +505,7 @@ def sub_config5(ctx, rank, world, timed, dist, steps=2):
     from spkdiar import _abi, sharded, synth
     rec = synth.config5(n_frames=C5_SEGMENTS * 173)
     sa, sb = [t[0] for t in rec.turns], [t[1] for t in rec.turns]
-    feat = ctx.upload(rec.frames)
+    feat = ctx.upload_frames(rec.frames)         # clustering only: no window statistics (K5 records from the frames)
     mbx = sharded.Mailboxes(ctx) if world > 1 else None
     box = {}
 

@@ -93,6 +93,14 @@ int  spkdiar_features_upload(spkdiar_ctx* ctx, const float* frames, int64_t n,
                              int32_t dim, spkdiar_feat** out);
 /* same, for a matrix that already lives in device memory (not copied, must
  * outlive the handle) */
+/* The same WITHOUT the window statistics (the 6,560 B-per-frame prefix records of K1): frames and shift only.
+ * What spk-clustering.py needs when it runs on its own (get_spk_features, spk-clustering.py:46-52: the frames
+ * of every turn, nothing per window): spkdiar_cluster_create / _run then accumulate the cluster records straight
+ * from the frames (156 B read per frame).  Any entry point that scores windows (spkdiar_gw_run,
+ * spkdiar_score_windows, spkdiar_score_sets, spkdiar_stats_window, spkdiar_cluster_batch) builds the
+ * statistics on first use, after which the handle behaves like one from spkdiar_features_upload. */
+int  spkdiar_features_upload_frames(spkdiar_ctx* ctx, const float* frames, int64_t n,
+                                    int32_t dim, spkdiar_feat** out);
 int  spkdiar_features_adopt(spkdiar_ctx* ctx, const float* dev_frames, int64_t n,
                             int32_t dim, spkdiar_feat** out);
 /* A BATCH of recordings in one handle (BASELINE config 4: spk-diarization2.py over a corpus,

@@ -39,7 +39,7 @@ SYMBOLS = (
     'spkdiar_ctx_exec',
     'spkdiar_replay_create', 'spkdiar_replay_free', 'spkdiar_replay_error', 'spkdiar_replay_info',
     'spkdiar_replay_chains', 'spkdiar_replay_segment', 'spkdiar_replay_turns', 'spkdiar_replay_cluster',
-    'spkdiar_replay_text',
+    'spkdiar_replay_text', 'spkdiar_features_upload_frames',
 )
 
 
@@ -100,6 +100,7 @@ def load_library(path=None):
         'spkdiar_profile_read': (C.c_int, [vp, pdbl, pi64]),
         'spkdiar_features_upload': (C.c_int, [vp, vp, i64, i32, C.POINTER(vp)]),
         'spkdiar_features_adopt': (C.c_int, [vp, vp, i64, i32, C.POINTER(vp)]),
+        'spkdiar_features_upload_frames': (C.c_int, [vp, vp, i64, i32, C.POINTER(vp)]),
         'spkdiar_stats_build': (C.c_int, [vp]),
         'spkdiar_features_free': (C.c_int, [vp]),
         'spkdiar_features_frames': (i64, [vp]),
@@ -348,6 +349,18 @@ class Context(object):
         h = C.c_void_p()
         self._check(self.lib.spkdiar_features_upload(self.h, frames.ctypes.data_as(C.c_void_p),
                                                      frames.shape[0], frames.shape[1], C.byref(h)))
+        return Features(self, h, frames.shape[0])
+
+    def upload_frames(self, frames):
+        """(n, 39) float32 host matrix -> Features WITHOUT window statistics (156 B per frame
+        resident instead of 6,716): for clustering on its own.  Cluster records then come
+        straight from the frames; the first call that scores windows builds the statistics."""
+        frames = np.ascontiguousarray(frames, dtype=np.float32)
+        if frames.ndim != 2:
+            raise ValueError('frames must be (n, dim)')
+        h = C.c_void_p()
+        self._check(self.lib.spkdiar_features_upload_frames(self.h, frames.ctypes.data_as(C.c_void_p),
+                                                            frames.shape[0], frames.shape[1], C.byref(h)))
         return Features(self, h, frames.shape[0])
 
     def upload_ptr(self, host_ptr, n, dim=DIM):

@@ -82,7 +82,9 @@ class Clusterer(object):
     def load(self, line):
         name = feature_file_name(line.audio, self.feapath, self.feaext, concat=self.variant == 1)
         dim, frames = read_features(name)
-        return self.ctx.upload(frames)
+        # clustering on its own never scores a window: frames only, cluster records straight from them
+        # (spk-clustering.py:46-52); `-m in` and KL2 score sets and build the window statistics on first use
+        return self.ctx.upload_frames(frames)
 
     @staticmethod
     def _range(turn, n):

@@ -27,6 +27,7 @@ struct spkdiar_clus {
     int metric = SPKDIAR_BIC;
     double lambda = 1.3;
     int64_t* seg = nullptr;      // device: a[n], b[n]
+    int64_t* hseg = nullptr;     // host copy (new[]): the direct records (K5) are planned on the host
     double* rec = nullptr;       // [n][REC]
     double* ld = nullptr;        // [n] ln|S_i|
     double* M = nullptr;         // [n][n]

@@ -67,9 +67,16 @@ struct spkdiar_feat {
     int32_t nrec = 0;
     void* tab = nullptr;          // device RecTab[nrec]
     int64_t max_tiles = 0;        // blocks of the longest recording
+    // spkdiar_features_upload_frames: P / C / tile / chunk are allocated and built on first use (P == nullptr
+    // until then); cluster records come straight from the frames meanwhile (K5, stats.cuh)
 };
 
 namespace spk {
+
+// spkdiar.cu: build the window statistics of a frames-only handle if they are missing (0 = ok)
+int ensure_stats(spkdiar_feat* f);
+// spkdiar.cu: records of the ranges [seg_a[k], seg_b[k]) (host arrays) into rec (device), from the frames (K5)
+int direct_records(spkdiar_feat* f, const int64_t* seg_a, const int64_t* seg_b, int64_t n, double* rec);
 
 inline int set_err(spkdiar_ctx* c, int code, const char* fmt, ...) {
     if (c) {

@@ -125,7 +125,24 @@ int spkdiar_profile_read(const spkdiar_ctx* c, double* ms, int64_t* launches) {
 
 // ---- features + K1 ------------------------------------------------------------------------
 
-static int feat_alloc(spkdiar_ctx* c, int64_t n, int32_t dim, spkdiar_feat** out, int32_t nrec = 0) {
+// the arrays of the window statistics (K1): 6,560 B per frame + the block level
+static int stats_alloc(spkdiar_feat* f) {
+    spkdiar_ctx* c = f->ctx;
+    const int32_t nrec = f->nrec;
+    cudaError_t e;
+    if ((e = pool_alloc(c, (size_t)(f->n + 1) * REC * sizeof(double), (void**)&f->P)) != cudaSuccess ||
+        (e = pool_alloc(c, (size_t)(f->ntiles + 1) * REC * sizeof(double2), (void**)&f->C)) != cudaSuccess ||
+        (e = pool_alloc(c, (size_t)std::max(nrec, 1) * K1_CHUNKS * REC * sizeof(double2), (void**)&f->chunk)) != cudaSuccess ||
+        (e = pool_alloc(c, (size_t)std::max<int64_t>(f->ntiles, 1) * REC * sizeof(double), (void**)&f->tile)) != cudaSuccess) {
+        pool_free(c, f->P); pool_free(c, f->C); pool_free(c, f->chunk); pool_free(c, f->tile);
+        f->P = nullptr; f->C = nullptr; f->chunk = nullptr; f->tile = nullptr;
+        return set_err(c, e == cudaErrorMemoryAllocation ? SPKDIAR_E_NOMEM : SPKDIAR_E_CUDA,
+                       "device allocation for the statistics of %lld frames failed: %s", (long long)f->n, cudaGetErrorString(e));
+    }
+    return SPKDIAR_OK;
+}
+
+static int feat_alloc(spkdiar_ctx* c, int64_t n, int32_t dim, spkdiar_feat** out, int32_t nrec = 0, bool with_stats = true) {
     if (!c || !out) return SPKDIAR_E_ARG;
     *out = nullptr;
     if (n < 0) return set_err(c, SPKDIAR_E_ARG, "negative frame count %lld", (long long)n);
@@ -138,28 +155,80 @@ static int feat_alloc(spkdiar_ctx* c, int64_t n, int32_t dim, spkdiar_feat** out
     if (!f) return set_err(c, SPKDIAR_E_NOMEM, "host allocation failed");
     f->ctx = c; f->n = n; f->dim = dim;
     f->ntiles = (n + K1_TILE - 1) / K1_TILE;
+    f->nrec = nrec;
     cudaError_t e;
-    if ((e = pool_alloc(c, (size_t)(n + 1) * REC * sizeof(double), (void**)&f->P)) != cudaSuccess ||
-        (e = pool_alloc(c, (size_t)(f->ntiles + 1) * REC * sizeof(double2), (void**)&f->C)) != cudaSuccess ||
-        (e = pool_alloc(c, (size_t)std::max(nrec, 1) * K1_XS * sizeof(double), (void**)&f->shift)) != cudaSuccess ||
-        (e = pool_alloc(c, (size_t)std::max(nrec, 1) * K1_CHUNKS * REC * sizeof(double2), (void**)&f->chunk)) != cudaSuccess ||
-        (e = pool_alloc(c, (size_t)std::max<int64_t>(f->ntiles, 1) * REC * sizeof(double), (void**)&f->tile)) != cudaSuccess) {
-        pool_free(c, f->P);
-        pool_free(c, f->C);
-        pool_free(c, f->shift);
-        pool_free(c, f->chunk);
+    if ((e = pool_alloc(c, (size_t)std::max(nrec, 1) * K1_XS * sizeof(double), (void**)&f->shift)) != cudaSuccess) {
         delete f;
         return set_err(c, e == cudaErrorMemoryAllocation ? SPKDIAR_E_NOMEM : SPKDIAR_E_CUDA,
                        "device allocation for %lld frames failed: %s", (long long)n, cudaGetErrorString(e));
+    }
+    if (with_stats) {
+        if (int rc = stats_alloc(f)) { pool_free(c, f->shift); delete f; return rc; }
     }
     *out = f;
     return SPKDIAR_OK;
 }
 
+extern "C++" {
+namespace spk {
+int ensure_stats(spkdiar_feat* f) {
+    if (!f) return SPKDIAR_E_ARG;
+    if (f->P) return SPKDIAR_OK;
+    if (int rc = stats_alloc(f)) return rc;
+    return spkdiar_stats_build(f);
+}
+
+int direct_records(spkdiar_feat* f, const int64_t* seg_a, const int64_t* seg_b, int64_t n, double* rec) {
+    spkdiar_ctx* c = f->ctx;
+    if (n <= 0) return SPKDIAR_OK;
+    // tasks of at most K5_SPAN frames; a range that needs several gets partial records and a reduction
+    std::vector<int64_t> ta, tb, td, rs, rp, rn;
+    int64_t nparts = 0;
+    for (int64_t k = 0; k < n; ++k) {
+        const int64_t len = seg_b[k] - seg_a[k];
+        const int64_t parts = len <= K5_SPAN ? 1 : (len + K5_SPAN - 1) / K5_SPAN;
+        if (parts == 1) { ta.push_back(seg_a[k]); tb.push_back(seg_b[k]); td.push_back(k); continue; }
+        rs.push_back(k); rp.push_back(nparts); rn.push_back(parts);
+        for (int64_t p = 0; p < parts; ++p) {
+            ta.push_back(seg_a[k] + p * K5_SPAN);
+            tb.push_back(std::min(seg_b[k], seg_a[k] + (p + 1) * K5_SPAN));
+            td.push_back(-(nparts + p) - 1);
+        }
+        nparts += parts;
+    }
+    const int64_t nt = (int64_t)ta.size(), nr = (int64_t)rs.size();
+    std::vector<int64_t> host((size_t)(3 * nt + 3 * nr));
+    std::copy(ta.begin(), ta.end(), host.begin());
+    std::copy(tb.begin(), tb.end(), host.begin() + nt);
+    std::copy(td.begin(), td.end(), host.begin() + 2 * nt);
+    std::copy(rs.begin(), rs.end(), host.begin() + 3 * nt);
+    std::copy(rp.begin(), rp.end(), host.begin() + 3 * nt + nr);
+    std::copy(rn.begin(), rn.end(), host.begin() + 3 * nt + 2 * nr);
+    DevBuf<int64_t> dtask; DevBuf<double> part;
+    SPK_CUDA(c, dtask.alloc(c, host.size()));
+    SPK_CUDA(c, part.alloc(c, (size_t)std::max<int64_t>(nparts, 1) * REC));
+    SPK_CUDA(c, cudaMemcpyAsync(dtask.p, host.data(), host.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    {
+        Prof p(c, SPKDIAR_PROF_STATS);
+        k5_direct<<<(unsigned)nt, K1_THREADS, 0, c->stream>>>(f->x, f->shift, dtask.p, nt, rec, part.p);
+        c->launches += 1;
+        if (nr > 0) {
+            k5_reduce<<<(unsigned)nr, K1_THREADS, 0, c->stream>>>(part.p, dtask.p + 3 * nt, nr, rec);
+            c->launches += 1;
+        }
+    }
+    SPK_CUDA(c, cudaGetLastError());
+    SPK_CUDA(c, cudaStreamSynchronize(c->stream));          // `host` and the two buffers are temporaries
+    return SPKDIAR_OK;
+}
+}  // namespace spk
+}  // extern "C++"
+
 int spkdiar_stats_build(spkdiar_feat* f) {
     if (!f) return SPKDIAR_E_ARG;
     spkdiar_ctx* c = f->ctx;
     SPK_CUDA(c, cudaSetDevice(c->device));
+    if (!f->P) { if (int rc = stats_alloc(f)) return rc; }
     {
         Prof p(c, SPKDIAR_PROF_STATS);
         if (f->nrec > 0) {
@@ -187,9 +256,18 @@ int spkdiar_stats_build(spkdiar_feat* f) {
     return SPKDIAR_OK;
 }
 
+static int upload_impl(spkdiar_ctx* c, const float* frames, int64_t n, int32_t dim, spkdiar_feat** out, bool with_stats);
+
 int spkdiar_features_upload(spkdiar_ctx* c, const float* frames, int64_t n, int32_t dim, spkdiar_feat** out) {
+    return upload_impl(c, frames, n, dim, out, true);
+}
+int spkdiar_features_upload_frames(spkdiar_ctx* c, const float* frames, int64_t n, int32_t dim, spkdiar_feat** out) {
+    return upload_impl(c, frames, n, dim, out, false);
+}
+
+static int upload_impl(spkdiar_ctx* c, const float* frames, int64_t n, int32_t dim, spkdiar_feat** out, bool with_stats) {
     if (!c || !out || (!frames && n > 0)) return c ? set_err(c, SPKDIAR_E_ARG, "null argument") : SPKDIAR_E_ARG;
-    int rc = feat_alloc(c, n, dim, out);
+    int rc = feat_alloc(c, n, dim, out, 0, with_stats);
     if (rc) return rc;
     spkdiar_feat* f = *out;
     float* dx = nullptr;
@@ -207,7 +285,14 @@ int spkdiar_features_upload(spkdiar_ctx* c, const float* frames, int64_t n, int3
         spkdiar_features_free(f); *out = nullptr;
         return set_err(c, SPKDIAR_E_CUDA, "feature upload failed: %s", cudaGetErrorString(e));
     }
-    rc = spkdiar_stats_build(f);
+    if (with_stats) {
+        rc = spkdiar_stats_build(f);
+    } else {
+        // the shift alone: the records of K5 are accumulated around it, like those of K1
+        if (n > 0) { k1_shift<<<1, 1024, 0, c->stream>>>(f->x, f->n, f->shift); c->launches += 1; }
+        else cudaMemsetAsync(f->shift, 0, K1_XS * sizeof(double), c->stream);
+        rc = cudaStreamSynchronize(c->stream) == cudaSuccess ? SPKDIAR_OK : set_err(c, SPKDIAR_E_CUDA, "feature upload failed");
+    }
     if (rc) { spkdiar_features_free(f); *out = nullptr; }
     return rc;
 }
@@ -291,6 +376,7 @@ int spkdiar_stats_window(spkdiar_feat* f, int64_t a, int64_t b, double* out819, 
     if (a < 0 || b < a || b > f->n) return set_err(c, SPKDIAR_E_ARG, "window [%lld,%lld) outside 0..%lld",
                                                   (long long)a, (long long)b, (long long)f->n);
     SPK_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = ensure_stats(f)) return rc;
     std::vector<double> ra(REC), rb(REC), ca(2 * REC), cb(2 * REC);
     SPK_CUDA(c, cudaMemcpyAsync(ra.data(), f->P + a * REC, REC * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SPK_CUDA(c, cudaMemcpyAsync(rb.data(), f->P + b * REC, REC * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -324,6 +410,7 @@ int spkdiar_score_windows(spkdiar_feat* f, const int64_t* a, const int64_t* m, c
             return set_err(c, SPKDIAR_E_ARG, "candidate %lld = (%lld,%lld,%lld) outside 0..%lld", (long long)k,
                            (long long)a[k], (long long)m[k], (long long)b[k], (long long)f->n);
     SPK_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = ensure_stats(f)) return rc;
     DevBuf<int64_t> idx; DevBuf<double> terms, dout;
     SPK_CUDA(c, idx.alloc(c, 3 * ncand));
     SPK_CUDA(c, terms.alloc(c, 3 * ncand));
@@ -375,6 +462,7 @@ int spkdiar_score_sets(spkdiar_feat* f, int64_t npairs,
                                (long long)r, side + 1, (long long)ra[r], (long long)rb[r], (long long)f->n);
     }
     SPK_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = ensure_stats(f)) return rc;
     DevBuf<int64_t> idx; DevBuf<double> rec, terms, dout;
     const int64_t nidx = 2 * (npairs + 1) + 2 * nr1 + 2 * nr2;
     SPK_CUDA(c, idx.alloc(c, nidx));

@@ -274,4 +274,43 @@ static __global__ void __launch_bounds__(K1_THREADS) k1_tile_write_batch(const f
                        tile + (t.base / K1_TILE) * REC, P + t.base * REC);
 }
 
+// ---- K5: statistics records of frame ranges straight from the frames ------------------------------
+// What get_spk_features + np.cov of the clustering scripts need (spk-clustering.py:46-52, 91-96): (n, sum x,
+// sum x x^T) of every initial cluster.  When no window search runs on the recording (spk-clustering.py started
+// on its own, BASELINE configs 3 and 5) the 6,560 B-per-frame prefix of K1 is never needed: a task = one range of
+// at most K5_SPAN frames, one CTA, thread q accumulates component q over the frames in order (same products, same
+// shift as K1), 156 B read per frame and one record written per range.  Longer ranges are cut into tasks whose
+// partial records k5_reduce adds in order.
+constexpr int64_t K5_SPAN = 4096;
+static __global__ void __launch_bounds__(K1_THREADS) k5_direct(const float* __restrict__ x, const double* __restrict__ shift,
+                                                        const int64_t* __restrict__ task, int64_t ntask,
+                                                        double* __restrict__ rec, double* __restrict__ part) {
+    __shared__ __align__(16) double xs[K1_TILE][K1_XS];
+    const int64_t a = task[blockIdx.x], b = task[ntask + blockIdx.x], dst = task[2 * ntask + blockIdx.x];
+    const int q = threadIdx.x;
+    const int r = q < REC ? c_row[q] : 0, c = q < REC ? c_col[q] : 0;
+    double acc = 0.0;
+    for (int64_t f0 = a; f0 < b; f0 += K1_TILE) {
+        __syncthreads();                               // the previous tile has been consumed
+        k1_load_tile(x, b, f0, shift, xs);             // frames at and past b count as absent
+        const int64_t left = b - f0;
+        const int valid = left < K1_TILE ? (int)left : K1_TILE;
+        if (q < REC) {
+#pragma unroll 4
+            for (int t = 0; t < valid; ++t) acc = fma(xs[t][r], xs[t][c], acc);
+        }
+    }
+    if (q < REC) (dst >= 0 ? rec + dst * REC : part + (-dst - 1) * REC)[q] = acc;
+}
+// red[0][k] = cluster, red[1][k] = its first partial record, red[2][k] = how many
+static __global__ void __launch_bounds__(K1_THREADS) k5_reduce(const double* __restrict__ part, const int64_t* __restrict__ red,
+                                                        int64_t nred, double* __restrict__ rec) {
+    const int64_t s = red[blockIdx.x], p0 = red[nred + blockIdx.x], np = red[2 * nred + blockIdx.x];
+    const int q = threadIdx.x;
+    if (q >= REC) return;
+    double acc = 0.0;
+    for (int64_t p = 0; p < np; ++p) acc += part[(p0 + p) * REC + q];
+    rec[s * REC + q] = acc;
+}
+
 }  // namespace spk

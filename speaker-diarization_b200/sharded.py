@@ -142,7 +142,8 @@ def cluster_sharded(ctx, frames_or_feat, seg_a, seg_b, metric, lambdac, threshol
     through peer memory; else ``exchange`` is called once per merge."""
     from . import _abi
     own = not isinstance(frames_or_feat, _abi.Features)
-    feat = ctx.upload(frames_or_feat) if own else frames_or_feat
+    # clustering only: frames without window statistics, cluster records straight from the frames
+    feat = ctx.upload_frames(frames_or_feat) if own else frames_or_feat
     try:
         with feat.cluster(seg_a, seg_b, metric, lambdac) as cl:
             if mailboxes is not None:

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 def _single(rec, a, b, metric, threshold, max_spk):
     with _abi.Context(0) as ctx:
-        f = ctx.upload(rec.frames)
+        f = ctx.upload_frames(rec.frames)           # as sharded.cluster_sharded uploads them
         with f.cluster(a, b, metric, 1.3) as cl:
             m, st = cl.run(threshold, max_spk, 1)
         f.close()
