@@ -231,7 +231,10 @@ int  spkdiar_selftest_stitch(uint64_t seed, double p_sync, int64_t nframes, int3
  * spk-clustering2.py:173-229 (variant 2).  Initial clusters are the frame
  * ranges [seg_a[k], seg_b[k]).  The device keeps per-cluster sufficient
  * statistics and the pair matrix resident and runs the merge loop without a
- * host round trip. */
+ * host round trip.  metric = SPKDIAR_BIC | _GLR | _KL2; for KL2 (spk-clustering.py:124-133) the
+ * engine caches diag(S), diag(S^-1) and the running float32 sum of every cluster (a merged
+ * cluster's sum continues a's over b's frames turn by turn, as np.mean of the concatenation
+ * does) - single GPU, spkdiar_cluster_run only. */
 typedef struct {
     int32_t a;          /* surviving cluster, index in the compacted list      */
     int32_t b;          /* removed cluster (a < b), same indexing              */

@@ -57,8 +57,8 @@ class Clusterer(object):
         self.min_det_dist = MAXINT
         self.speakers = []
         self.merges = []               # (a, b, d) in compacted indices, as logged
-        # 'device': resident engine (BIC, GLR); 'host': merge loop on the host with
-        # every distance from the device (KL2, and the cross-check in the tests)
+        # 'device': resident engine (BIC, GLR, KL2); 'host': merge loop on the host with
+        # every distance from the device (the cross-check in the tests)
         self.engine = engine
         self._own_ctx = ctx is None
         self.ctx = ctx if ctx is not None else _abi.Context(device)
@@ -228,7 +228,7 @@ class Clusterer(object):
     def _cluster_hi(self, feat, recipe, outf, segf):
         """CL1:178-260 / CL2:173-229."""
         speakers = self.speakers
-        use_device = self.engine == 'device' and self.metric != _abi.KL2
+        use_device = self.engine == 'device'
         merges = self._merge_sequence_device(feat) if use_device else self._merge_sequence_host(feat)
         for a, b, d in merges:
             if not self.quiet:

@@ -32,6 +32,11 @@ struct spkdiar_clus {
     double* ld = nullptr;        // [n] ln|S_i|
     double* M = nullptr;         // [n][n]
     uint8_t* alive = nullptr;    // [n] (final state, for the test hook)
+    // KL2 (spk-clustering.py:124-133): per cluster diag(S), diag(S^-1) and the running float32 sum of its frames in
+    // the order the reference concatenates them; the turns of a cluster as a linked list of initial segments
+    double* kside = nullptr;     // [n][KS]
+    float* ksum = nullptr;       // [n][VS]
+    int32_t* klist = nullptr;    // [3][n]: next segment, head and tail of cluster
     bool ran = false;
     double* rowlog_host = nullptr;   // test hook (spkdiar_cluster_rowlog): row a after every merge
     int64_t rowlog_cap = 0;
@@ -236,6 +241,9 @@ struct ClDev {
                                  // sets 0 / 1: candidates of even / odd merges, set 2: the final statistics round
     unsigned long long seq_base; // sequence numbers of this run start above it
     int* err;                    // set when a peer did not answer in time
+    // KL2 (single GPU): cached sides and running sums per cluster, turn lists, the frames
+    double* kside; float* ksum; int32_t* knext; int32_t* khead; int32_t* ktail;
+    const float* x; const int64_t* seg;
 };
 
 __device__ __forceinline__ void cl_grid_barrier(unsigned long long* ctr, unsigned long long& target) {
@@ -252,7 +260,7 @@ __device__ __forceinline__ void cl_grid_barrier(unsigned long long* ctr, unsigne
 
 // shared memory of the merge kernels: per-warp scratch, merged record [REC], small arrays, alive bitmask
 struct ClSmem {
-    WarpScratch* ws; double* merged; ClBest* wbest; double* shd; int* wbusy; uint32_t* abits;
+    WarpScratch* ws; double* merged; ClBest* wbest; double* shd; int* wbusy; double* kside; float* ksum; uint32_t* abits;
 };
 __device__ __forceinline__ ClSmem cl_carve(unsigned char* base) {
     ClSmem m;
@@ -261,11 +269,79 @@ __device__ __forceinline__ ClSmem cl_carve(unsigned char* base) {
     m.wbest = reinterpret_cast<ClBest*>(m.merged + REC);
     m.shd = reinterpret_cast<double*>(m.wbest + CL_WARPS);          // [0] ld_ab
     m.wbusy = reinterpret_cast<int*>(m.shd + 2);                    // [CL_WARPS] warp has a pair in round 0
-    m.abits = reinterpret_cast<uint32_t*>(m.wbusy + CL_WARPS);
+    m.kside = reinterpret_cast<double*>(m.wbusy + CL_WARPS);        // [KS] KL2: side of the merged cluster
+    m.ksum = reinterpret_cast<float*>(m.kside + KS);                // [VS] ... and its running sum
+    m.abits = reinterpret_cast<uint32_t*>(m.ksum + VS);
     return m;
 }
 __device__ __forceinline__ bool cl_own(const ClDev& g, int64_t r, int64_t c) {
     return g.nranks == 1 || (int32_t)((r + c) % g.nranks) == g.rank;
+}
+
+// ---------- KL2 in the clustering engine ----------
+// the scratch kl2_side_one wants, laid over a warp's WarpScratch (operand buffer 0 = record / factor, buffer 1 = 1 / pivots)
+struct ClKl2Scr { LdlScratch& w; double* rec; double* pinv; };
+__device__ __forceinline__ ClKl2Scr cl_kl2_scr(WarpScratch& ws) { return ClKl2Scr{ws, ws.rec[0], ws.rec[1]}; }
+
+// np.mean of a float32 matrix sums row after row: continue the running sum (s0, s1) of lane's
+// dimensions over the frames [a, b), sixteen loads in flight
+__device__ __forceinline__ void cl_kl2_add_rows(const float* __restrict__ x, int64_t a, int64_t b, int lane, float& s0, float& s1) {
+    const int off2 = lane + 32 < D39 ? 32 : 0;
+    const float* row = x + a * D39 + lane;
+    const int64_t nrow = b - a;
+    for (int64_t r0 = 0; r0 < nrow; r0 += 16) {
+        float u[16], v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const bool ok = r0 + q < nrow;
+            u[q] = ok ? __ldg(row + (r0 + q) * D39) : 0.f;
+            v[q] = ok ? __ldg(row + (r0 + q) * D39 + off2) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if (r0 + q < nrow) { s0 = __fadd_rn(s0, u[q]); s1 = __fadd_rn(s1, v[q]); }
+    }
+}
+
+// initial clusters: side and running sum of segment s, one warp each
+static __global__ void __launch_bounds__(SC_THREADS, 3)
+cl_kl2_init(const double* __restrict__ rec, const float* __restrict__ x, const int64_t* __restrict__ seg, int64_t n,
+            double* __restrict__ kside, float* __restrict__ ksum, int32_t* __restrict__ klist) {
+    extern __shared__ __align__(16) unsigned char sc_smem[];
+    WarpScratch* ws = reinterpret_cast<WarpScratch*>(sc_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t s = (int64_t)blockIdx.x * SC_WARPS + warp; s < n; s += (int64_t)gridDim.x * SC_WARPS) {
+        ClKl2Scr k = cl_kl2_scr(ws[warp]);
+        __shared__ double side[SC_WARPS][KS];
+        kl2_side_one(RecSrc{rec + s * REC}, k, side[warp], side[warp] + VS, lane);
+        for (int q = lane; q < KS; q += 32) kside[s * KS + q] = (q % VS) < D39 ? side[warp][q] : 0.0;
+        float s0 = 0.f, s1 = 0.f;
+        cl_kl2_add_rows(x, seg[s], seg[n + s], lane, s0, s1);
+        ksum[s * VS + lane] = s0;
+        if (lane + 32 < D39) ksum[s * VS + lane + 32] = s1;
+        if (lane == 0) { klist[s] = -1; klist[n + s] = (int32_t)s; klist[2 * n + s] = (int32_t)s; }
+        __syncwarp();
+    }
+}
+
+// initial fill with the KL2 distances, one warp per pair (cached sides: no factorisation here)
+static __global__ void __launch_bounds__(256)
+cl_fill_pairs_kl2(const double* __restrict__ rec, const double* __restrict__ kside, const float* __restrict__ ksum, int64_t n,
+                  int variant, double* __restrict__ M, unsigned long long* stat) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t npair = (n * (n - 1)) / 2;
+    ClTrack track;
+    for (int64_t p = (int64_t)blockIdx.x * 8 + warp; p < npair; p += (int64_t)gridDim.x * 8) {
+        int64_t i, j;
+        cl_pair(p, n, i, j);
+        const double d = kl2_distance_cached(kside + i * KS, kside + j * KS, ksum + i * VS, ksum + j * VS,
+                                             rec[i * REC + L39::CNT], rec[j * REC + L39::CNT], lane);
+        if (lane == 0) {
+            M[i * n + j] = d;
+            if (variant == 1) { M[j * n + i] = d; track.see(d); }
+        }
+    }
+    if (lane == 0) track.flush(stat);
 }
 
 // ---------- ARGMIN over the alive (owned) part of the matrix, from the row-minimum cache ----------
@@ -411,11 +487,29 @@ __device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, i
     int64_t ord = gwarp;
     int64_t k = select(ord);
     auto mine_pair = [&](int64_t kk) { return kk < n && kk != a && cl_own(g, a, kk); };
-    if (lane == 0) sm.wbusy[warp] = mine_pair(k) ? 1 : 0;
+    const bool kl2 = g.metric == SPKDIAR_KL2;
+    if (kl2) {
+        // KL2 (spk-clustering.py:124-133): a pair costs no factorisation - diag(S), diag(S^-1) and the float32
+        // sum of every cluster are cached.  What the merge needs first: the side of the merged cluster (warp 0,
+        // one factorisation + inverse) and its running sum, a's sum continued over b's frames turn by turn in the
+        // order the reference concatenates them (warp 1).  Every CTA does both itself: no broadcast.
+        if (warp == 0) {
+            ClKl2Scr scr = cl_kl2_scr(sm.ws[0]);
+            kl2_side_one(X, scr, sm.kside, sm.kside + VS, lane);
+        } else if (warp == 1) {
+            float s0 = __ldcg(g.ksum + a * VS + lane), s1 = lane + 32 < D39 ? __ldcg(g.ksum + a * VS + lane + 32) : 0.f;
+            for (int32_t s = __ldcg(g.khead + b); s >= 0; s = __ldcg(g.knext + s))
+                cl_kl2_add_rows(g.x, g.seg[s], g.seg[n + s], lane, s0, s1);
+            sm.ksum[lane] = s0;
+            if (lane + 32 < D39) sm.ksum[lane + 32] = s1;
+        }
+    }
+    if (lane == 0) sm.wbusy[warp] = (kl2 || mine_pair(k)) ? 1 : 0;
     __syncthreads();
     int ldw = 0;
 #pragma unroll
     for (int w = CL_WARPS - 1; w >= 0; --w) if (!sm.wbusy[w]) ldw = w;
+    if (kl2) ldw = -1;                            // nobody computes ln|S_ab|
     const double N1 = sm.merged[L39::CNT];
     double ld_ab = 0.0;
     ClBest rowa{d_inf(), INT64_MAX};             // lane 0: best (distance, k) this warp produced for row a
@@ -432,22 +526,26 @@ __device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, i
         int32_t cmin = -1;
         if (has && term == 2 && lane == 0) {
             N2 = __ldcg(g.rec + kk * REC + L39::CNT);
-            ldk = __ldcg(g.ld + kk);
+            if (!kl2) ldk = __ldcg(g.ld + kk);
             cmin = __ldcg(g.rowmin_c + kk);
             if (g.variant == 1) vold = __ldcg(g.rowmin_v + kk);
         }
-        if (has) {
+        double dk = 0.0;
+        if (has && kl2) {
+            N2 = __shfl_sync(0xffffffffu, N2, 0);
+            dk = kl2_distance_cached<true>(sm.kside, g.kside + kk * KS, sm.ksum, g.ksum + kk * VS, N1, N2, lane);
+        } else if (has) {
             const RecSrc Y{g.rec + kk * REC};
             t = logdet_term(term, g.metric, X, Y, sm.ws[warp], lane);
         }
-        if (round == 0) {
+        if (round == 0 && !kl2) {
             if (warp == ldw && lane == 0) sm.shd[0] = t;
             __syncthreads();
             ld_ab = sm.shd[0];
         }
         if (has && term == 2 && lane == 0) {
-            const double d = g.metric == SPKDIAR_BIC ? bic_combine(N1, N2, ld_ab, ldk, t, g.lambda)
-                                                     : glr_combine(N1, N2, ld_ab, ldk, t);
+            const double d = kl2 ? dk : (g.metric == SPKDIAR_BIC ? bic_combine(N1, N2, ld_ab, ldk, t, g.lambda)
+                                                                 : glr_combine(N1, N2, ld_ab, ldk, t));
             g.M[a * n + kk] = d;                                            // row a
             cl_take(rowa, d, kk);                                            // minimum of the new row a
             bool flag = false;
@@ -609,6 +707,14 @@ static __global__ void __launch_bounds__(CL_THREADS, 1) cl_merge_loop(const ClDe
         if (blockIdx.x == 0) {
             for (int q = threadIdx.x; q < REC; q += CL_THREADS) g.rec[a * REC + q] = sm.merged[q];
             if (threadIdx.x == 0) g.ld[a] = ld_ab;
+            if (g.metric == SPKDIAR_KL2) {
+                for (int q = threadIdx.x; q < KS; q += CL_THREADS) g.kside[a * KS + q] = (q % VS) < D39 ? sm.kside[q] : 0.0;
+                if (threadIdx.x < D39) g.ksum[a * VS + threadIdx.x] = sm.ksum[threadIdx.x];
+                if (threadIdx.x == 0) {                      // a's turns, then b's (spk-clustering.py:218: extend)
+                    g.knext[g.ktail[a]] = g.khead[b];
+                    g.ktail[a] = g.ktail[b];
+                }
+            }
         }
         if (g.rowlog && nm < g.rowlog_cap)                  // test hook: the rewritten row, for the host's argmin replay
             for (int64_t cidx = (int64_t)blockIdx.x * CL_THREADS + threadIdx.x; cidx < n; cidx += (int64_t)gridDim.x * CL_THREADS)
@@ -813,7 +919,7 @@ static __global__ void cl_alive_max(const double* __restrict__ M, const uint8_t*
 
 inline size_t cl_smem_bytes(int64_t n) {
     return CL_WARPS * sizeof(WarpScratch) + REC * sizeof(double) + CL_WARPS * sizeof(ClBest) + 2 * sizeof(double)
-           + CL_WARPS * sizeof(int)
+           + CL_WARPS * sizeof(int) + KS * sizeof(double) + VS * sizeof(float)
            + (size_t)((n + 31) / 32) * sizeof(uint32_t) + 16;
 }
 
@@ -830,6 +936,8 @@ cudaError_t cluster_configure() {
     e = cudaFuncSetAttribute(cl_shard_apply_dev, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(cl_fill_pairs_shard, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(cl_kl2_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(cl_self_logdet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM);
     if (e != cudaSuccess) return e;

@@ -55,7 +55,6 @@ constexpr int GW_JMAX = 160;            // fine-tune candidates (2*istep + 1 <= 
                                         // a fine tune of window 0 could look at)
 #define GW_NEG_INIT (-9223372036854775808.0)   /* -sys.maxint - 1 as a double, CD:203 */
 
-constexpr int KS = 2 * VS;              // doubles per cached KL2 side: diag(S)[40], diag(S^-1)[40]
 constexpr int GW_RING_ROWS = 64;        // frame rows per ring stage (a multiple of 4: 16-byte spans)
 constexpr int GW_RING_STAGES = 6;
 constexpr int GW_STAGE_FLOATS = GW_RING_ROWS * D39;
@@ -424,28 +423,6 @@ __device__ __forceinline__ GwChain gw_make_chain(const GwChainCtx& c, int ct, in
     return ch;
 }
 
-// distance of one KL2 candidate from its two cached sides and running sums (one warp)
-__device__ __forceinline__ double gw_kl2_distance(const double* sideL, const double* sideR,
-                                                  const float* sumL, const float* sumR,
-                                                  double nL, double nR, int lane) {
-    double t1 = 0.0, t2 = 0.0;
-    const float fl = (float)nL, fr = (float)nR;
-    for (int j = lane; j < D39; j += 32) {
-        const float m0 = __fdiv_rn(__ldcg(sumL + j), fl), m1 = __fdiv_rn(__ldcg(sumR + j), fr);
-        const double delta = (double)__fsub_rn(m0, m1);
-        const double s0 = __ldcg(sideL + j), p0 = __ldcg(sideL + VS + j);
-        const double s1 = __ldcg(sideR + j), p1 = __ldcg(sideR + VS + j);
-        t1 += (s0 - s1) * (p1 - p0);
-        t2 += __dmul_rn(__dmul_rn(p0 + p1, delta), delta);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
-        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
-    }
-    return __dadd_rn(__dmul_rn(0.5, t1), __dmul_rn(0.5, t2));
-}
-
 // candidate offset k: the host table, or its closed form when the host found the
 // table to BE minfeas + k * istep exactly (dyadic frame rates such as 100 or 125 fps)
 __device__ __forceinline__ double gw_T(const GwDev& g, int64_t k) {
@@ -787,7 +764,7 @@ static __global__ void __launch_bounds__(GW_THREADS, 1) gw_kernel(const GwDev g)
                         mr = ksum_fine + ((int64_t)(parity * 2 + 1) * GW_JMAX + t) * VS;
                         dst = fine + (int64_t)parity * 3 * GW_JMAX + t;
                     }
-                    const double v = gw_kl2_distance(sl, sr, ml, mr, (double)(mm - s0), (double)(ee - mm), lane);
+                    const double v = kl2_distance_cached(sl, sr, ml, mr, (double)(mm - s0), (double)(ee - mm), lane);
                     if (lane == 0) *dst = v;
                 }
             } else {

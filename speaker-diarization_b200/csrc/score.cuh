@@ -237,6 +237,33 @@ __device__ __forceinline__ double kl2_finish(Kl2Scratch& k, int lane, double* t1
     return __dadd_rn(__dmul_rn(0.5, t1), __dmul_rn(0.5, t2));
 }
 
+constexpr int KS = 2 * VS;              // doubles per cached KL2 side: diag(S)[40], diag(S^-1)[40]
+
+// distance of one KL2 pair from the two cached sides (diag S [VS], diag S^-1 [VS]) and running float32 sums
+// (one warp; the growing-window search caches them per offset, the clustering engine per cluster)
+// (LSHARED: the left side and sum sit in shared memory - the merged cluster of the clustering engine)
+template <bool LSHARED = false>
+__device__ __forceinline__ double kl2_distance_cached(const double* sideL, const double* sideR,
+                                                  const float* sumL, const float* sumR,
+                                                  double nL, double nR, int lane) {
+    double t1 = 0.0, t2 = 0.0;
+    const float fl = (float)nL, fr = (float)nR;
+    for (int j = lane; j < D39; j += 32) {
+        const float m0 = __fdiv_rn(LSHARED ? sumL[j] : __ldcg(sumL + j), fl), m1 = __fdiv_rn(__ldcg(sumR + j), fr);
+        const double delta = (double)__fsub_rn(m0, m1);
+        const double s0 = LSHARED ? sideL[j] : __ldcg(sideL + j), p0 = LSHARED ? sideL[VS + j] : __ldcg(sideL + VS + j);
+        const double s1 = __ldcg(sideR + j), p1 = __ldcg(sideR + VS + j);
+        t1 += (s0 - s1) * (p1 - p0);
+        t2 += __dmul_rn(__dmul_rn(p0 + p1, delta), delta);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    }
+    return __dadd_rn(__dmul_rn(0.5, t1), __dmul_rn(0.5, t2));
+}
+
 static __global__ void __launch_bounds__(SC_THREADS, 2)
 win_kl2_kernel(const Stats st, const float* __restrict__ x,
                const int64_t* __restrict__ a, const int64_t* __restrict__ m,

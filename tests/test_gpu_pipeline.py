@@ -168,6 +168,31 @@ def test_device_merge_loop_equals_host_driven_loop(variant, dist, thr, ctx):
         feat.close()
 
 
+@pytest.mark.parametrize('variant', [1, 2])
+def test_device_merge_loop_scores_kl2(variant, ctx):
+    """KL2 inside the resident engine (cached diag S, diag S^-1 and running float32 sums per cluster, the sum of a
+    merged cluster continued turn by turn, spk-clustering.py:124-133, 216-237) against the host-driven loop, which
+    scores every pair from the frame ranges: same merges, distances to rounding, same recipe."""
+    rec = synth.make_recording(302, 12000, 5, turn_lo=1, turn_hi=4)
+    feat = ctx.upload(rec.frames)
+    recipe = [Line('/x.wav', 'a_%d' % (k + 1), a / 100.0, b / 100.0) for k, (a, b, _) in enumerate(rec.turns)]
+    try:
+        res = []
+        for engine in ('device', 'host'):
+            cl = pcl.Clusterer(100, variant, 'hi', 'KL2', -1.0, 3, 1.3, ctx=ctx, engine=engine)
+            out = io.StringIO()
+            cl.process_recipe(recipe, out, loader=lambda l: feat)
+            res.append((out.getvalue(), [(a, b) for a, b, _ in cl.merges], [d for _, _, d in cl.merges],
+                        cl.max_dist, cl.min_dist))
+        assert len(res[0][1]) == len(rec.turns) - 3
+        assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
+        assert np.allclose(res[0][2], res[1][2], rtol=1e-9, atol=0)
+        assert np.isclose(float(res[0][3]), float(res[1][3]), rtol=1e-9)
+        assert np.isclose(float(res[0][4]), float(res[1][4]), rtol=1e-9)
+    finally:
+        feat.close()
+
+
 def test_clustering_max_spk_forces_merges(tmp_path, ctx):
     rpath, feadir, rec = _case(tmp_path, 41, 7000, 4, kind='turns', turn_lo=2, turn_hi=5)
     for variant in (1, 2):
