@@ -302,10 +302,20 @@ __device__ __forceinline__ double ldl_logdet(double (&a)[Grid<D>::NSLOT], LdlScr
     if (D > 32) s += log(p1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    // NaN when a pivot is not > 0 (a log alone would let a last pivot of exactly 0 through as -inf)
-    const bool bad = __any_sync(0xffffffffu, !(p0 > 0.0) || !(p1 > 0.0));
+    // A pivot that is not > 0: the matrix is singular to working precision (a cluster of fewer frames than
+    // dimensions, a constant feature) or the input was not finite.  The reference takes np.log(det(S)) of such a
+    // matrix: LAPACK's determinant underflows to 0 (-inf, and the pair distance +inf, which the agglomeration
+    // ignores) or comes out as rounding noise of either sign - nothing to reproduce bit for bit.  Ruling: the
+    // FIRST pivot that fails decides - NaN if it is NaN (non-finite input), -inf otherwise (det -> 0); pivots
+    // after it are garbage either way.  (A NaN here would stop the whole agglomeration: ndarray.argmin returns
+    // the first NaN and `mind <= threshold` is False, spk-clustering.py:203-208.)
+    const unsigned m0 = __ballot_sync(0xffffffffu, !(p0 > 0.0)), m1 = __ballot_sync(0xffffffffu, !(p1 > 0.0));
     __syncwarp();
-    return bad ? __longlong_as_double(0x7ff8000000000000LL) : s;
+    if (m0 | m1) {
+        const double first = m0 ? __shfl_sync(0xffffffffu, p0, __ffs(m0) - 1) : __shfl_sync(0xffffffffu, p1, __ffs(m1) - 1);
+        return first != first ? __longlong_as_double(0x7ff8000000000000LL) : -__longlong_as_double(0x7ff0000000000000LL);
+    }
+    return s;
 }
 
 // ---- factorisation fused with the inverse of the factor (KL2) -------------
@@ -452,6 +462,8 @@ __device__ __forceinline__ double ldl_logdet_inv(double (&a)[Grid<D>::NSLOT], Ld
 // mapping of np.log(det(S)): a determinant that under/overflows
 // fp64 makes the reference see -inf / +inf.
 __device__ __forceinline__ double finish_logdet(double ln_m, double n, int d) {
+    // no more frames than dimensions: the covariance is singular by construction (see ldl_logdet)
+    if (n > 1.0 && n <= (double)d) return -__longlong_as_double(0x7ff0000000000000LL);
     double v = ln_m - (double)d * log(n - 1.0);
     if (v < -744.4400719213812) v = -__longlong_as_double(0x7ff0000000000000LL);
     else if (v > 709.782712893384) v = __longlong_as_double(0x7ff0000000000000LL);

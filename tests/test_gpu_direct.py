@@ -100,3 +100,32 @@ def test_frames_only_sharded_run_equals_resident(ctx):
     assert not err, err
     for m, _ in out:
         assert m.tobytes() == want.tobytes()
+
+
+def test_cluster_of_fewer_frames_than_dimensions_stays_alone(ctx):
+    """A turn of 30 frames in 39 dimensions has a singular covariance: the reference's np.log(det(S)) is -inf
+    (the determinant underflows) or rounding noise; the ruling here is -inf, i.e. a pair distance of +inf that the
+    agglomeration ignores - the other clusters merge as if the short turn were not there (a NaN instead would
+    stop the loop at once: ndarray.argmin returns the first NaN, spk-clustering.py:203-208)."""
+    rec = synth.make_recording(91, 20000, 3, turn_lo=3, turn_hi=6)
+    sa, sb = [t[0] for t in rec.turns], [t[1] for t in rec.turns]
+    short = len(sa) // 2
+    sa2 = sa[:short] + [sa[short]] + sa[short + 1:]
+    sb2 = sb[:short] + [sa[short] + 30] + sb[short + 1:]
+    for upload in (ctx.upload, ctx.upload_frames):
+        with upload(rec.frames) as feat:
+            with feat.cluster(sa, sb, _abi.BIC, 1.3) as cl:
+                full, _ = cl.run(0.0, 0, 1)
+            with feat.cluster(sa2, sb2, _abi.BIC, 1.3) as cl:
+                got, _ = cl.run(0.0, 0, 1)
+                M, alive = cl.matrix()
+        assert len(full) > 5
+        assert len(got) >= len(full) - 2 and np.all(np.isfinite(got['d']))
+        # nobody merged with the short turn; every distance to it is +inf
+        members = [[k] for k in range(len(sa2))]
+        for m in got:
+            members[m['a']].extend(members[m['b']])
+            members.pop(m['b'])
+        assert [short] in members
+        row = M[short][alive.astype(bool)]
+        assert np.all(np.isposinf(np.delete(row, np.flatnonzero(np.flatnonzero(alive) == short))))
