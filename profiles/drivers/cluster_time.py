@@ -20,7 +20,7 @@ else:
     rec = synth.config5(n_frames=nseg * 173)
 print('generated %d frames, %d segments in %.1f s' % (rec.frames.shape[0], len(rec.turns), time.perf_counter() - t0), flush=True)
 ctx = _abi.Context(0)
-f = ctx.upload(rec.frames)
+f = ctx.upload_frames(rec.frames) if os.environ.get('SPKDIAR_FRAMES_ONLY', '1') != '0' else ctx.upload(rec.frames)
 a = [t[0] for t in rec.turns]
 b = [t[1] for t in rec.turns]
 for rep in range(2):

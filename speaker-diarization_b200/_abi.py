@@ -349,7 +349,7 @@ class Context(object):
         h = C.c_void_p()
         self._check(self.lib.spkdiar_features_upload(self.h, frames.ctypes.data_as(C.c_void_p),
                                                      frames.shape[0], frames.shape[1], C.byref(h)))
-        return Features(self, h, frames.shape[0])
+        return Features(self, h, frames.shape[0], frames.shape[1])
 
     def upload_frames(self, frames):
         """(n, 39) float32 host matrix -> Features WITHOUT window statistics (156 B per frame
@@ -361,27 +361,31 @@ class Context(object):
         h = C.c_void_p()
         self._check(self.lib.spkdiar_features_upload_frames(self.h, frames.ctypes.data_as(C.c_void_p),
                                                             frames.shape[0], frames.shape[1], C.byref(h)))
-        return Features(self, h, frames.shape[0])
+        return Features(self, h, frames.shape[0], frames.shape[1])
 
     def upload_ptr(self, host_ptr, n, dim=DIM):
         """Same from a raw host pointer (e.g. pinned torch memory)."""
         h = C.c_void_p()
         self._check(self.lib.spkdiar_features_upload(self.h, C.c_void_p(host_ptr), n, dim, C.byref(h)))
-        return Features(self, h, n)
+        return Features(self, h, n, dim)
 
     def upload_batch(self, matrices):
         """A batch of recordings -> FeaturePack (one packed handle, statistics restarting per
         recording).  ``matrices``: (n_r, 39) float32 arrays, or (host pointer, n_r) pairs
         (e.g. pinned torch memory)."""
         keep, ptrs, ns = [], [], []
+        dim = None                       # (host pointer, n) pairs carry DIM-dimensional rows
         for m in matrices:
             if isinstance(m, tuple):
                 ptrs.append(int(m[0]))
                 ns.append(int(m[1]))
             else:
                 m = np.ascontiguousarray(m, dtype=np.float32)
-                if m.ndim != 2 or m.shape[1] != DIM:
-                    raise SpkdiarError(-5, 'feature dimension %r: the kernels are specialised for %d' % (m.shape, DIM))
+                if m.ndim != 2 or not 1 <= m.shape[1] <= DIM:
+                    raise SpkdiarError(-5, 'feature matrix of shape %r: the kernels handle 1..%d dimensions' % (m.shape, DIM))
+                if dim is not None and m.shape[1] != dim:
+                    raise SpkdiarError(-2, 'recordings of %d and %d dimensions in one batch' % (dim, m.shape[1]))
+                dim = m.shape[1]
                 keep.append(m)
                 ptrs.append(m.ctypes.data)
                 ns.append(m.shape[0])
@@ -390,24 +394,25 @@ class Context(object):
         n = np.array(ns, dtype=np.int64)
         base = np.zeros(max(nrec, 1), dtype=np.int64)
         h = C.c_void_p()
-        self._check(self.lib.spkdiar_features_upload_batch(self.h, arr, _p(n, C.c_int64), nrec, DIM,
+        self._check(self.lib.spkdiar_features_upload_batch(self.h, arr, _p(n, C.c_int64), nrec, dim or DIM,
                                                            C.byref(h), _p(base, C.c_int64)))
-        return FeaturePack(self, h, base[:nrec].tolist(), ns)
+        return FeaturePack(self, h, base[:nrec].tolist(), ns, dim or DIM)
 
     def adopt(self, dev_ptr, n, dim=DIM):
         """Features over a matrix already in device memory (not copied)."""
         h = C.c_void_p()
         self._check(self.lib.spkdiar_features_adopt(self.h, C.c_void_p(dev_ptr), n, dim, C.byref(h)))
-        return Features(self, h, n)
+        return Features(self, h, n, dim)
 
 
 class Features(object):
     """``spkdiar_feat``: frames + prefix statistics resident in HBM."""
 
-    def __init__(self, ctx, handle, n):
+    def __init__(self, ctx, handle, n, dim=DIM):
         self.ctx = ctx
         self.h = handle
         self.n = int(n)
+        self.dim = int(dim)              # of the feature file (<= 39; the device keeps 39 zero-padded columns)
         ctx.live_features = getattr(ctx, 'live_features', 0) + 1
         ctx.peak_features = max(getattr(ctx, 'peak_features', 0), ctx.live_features)
 
@@ -590,8 +595,8 @@ class FeaturePack(Features):
     """A batch of recordings in one handle (``spkdiar_features_upload_batch``).  Positions on
     the pack itself are packed frame rows; ``view(r)`` is recording r with its own positions."""
 
-    def __init__(self, ctx, handle, base, n):
-        Features.__init__(self, ctx, handle, (base[-1] + (n[-1] // 128 + 1) * 128) if n else 0)
+    def __init__(self, ctx, handle, base, n, dim=DIM):
+        Features.__init__(self, ctx, handle, (base[-1] + (n[-1] // 128 + 1) * 128) if n else 0, dim)
         self.base = list(base)
         self.lengths = list(n)
 
@@ -658,6 +663,7 @@ class FeatureView(object):
         self.r = int(r)
         self.off = int(pack.base[r])
         self.n = int(pack.lengths[r])
+        self.dim = getattr(pack, 'dim', DIM)
 
     def close(self):
         pass

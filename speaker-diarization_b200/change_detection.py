@@ -119,6 +119,7 @@ class Detector(object):
         self._own_ctx = ctx is None
         self.ctx = ctx if ctx is not None else _abi.Context(device)
         self.windows_visited = 0
+        self.dim = _abi.DIM            # of the feature file in use (set when it is loaded)
         self._prefetch = {}
 
     def close(self):
@@ -248,7 +249,7 @@ class Detector(object):
             d, m, s0, e0 = self._score_offsets(feat, a, start, end, off)
             for dk, mk in zip(d, m):
                 if _is_inf(dk):
-                    self.log(p2line('Inf:', (mk - s0, _abi.DIM), (e0 - mk, _abi.DIM), dk))
+                    self.log(p2line('Inf:', (mk - s0, feat.dim), (e0 - mk, feat.dim), dk))
 
     def _gw_host_driven(self, feat, line, a, b, outf, segf):
         """The same search with the LOOP on the host and every distance on the
@@ -279,7 +280,7 @@ class Detector(object):
                         maxd = dk
                         maxi = i
                     elif _is_inf(dk):
-                        self.log(p2line('Inf:', (mk - s0, _abi.DIM), (e0 - mk, _abi.DIM), dk))
+                        self.log(p2line('Inf:', (mk - s0, feat.dim), (e0 - mk, feat.dim), dk))
             st.window(maxd)
             if maxd > self.threshold and not _is_inf(maxd):
                 fine = []
@@ -293,7 +294,7 @@ class Detector(object):
                         maxd = dk
                         maxi = i
                     elif _is_inf(dk):
-                        self.log(p2line('Inf:', (mk - s0, _abi.DIM), (e0 - mk, _abi.DIM), dk))
+                        self.log(p2line('Inf:', (mk - s0, feat.dim), (e0 - mk, feat.dim), dk))
                 self.writer.write(line, start, start + maxi, line.start, 'spk_turn', outf, segf)
                 st.detected(maxd)
                 start += maxi
@@ -380,11 +381,11 @@ class Detector(object):
         """BIC through the shared memo of CD:72 (Q2) or, with ``--bic-cache
         correct``, on the window's own left term."""
         if self.bic_cache == 'reference':
-            d, c1 = bic_from_terms(n1, n2, terms[0], terms[1], terms[2], self.lambdac, self.memo_c1)
+            d, c1 = bic_from_terms(n1, n2, terms[0], terms[1], terms[2], self.lambdac, self.memo_c1, p=self.dim)
             if self.memo_c1 is None:
                 self.memo_c1 = c1
             return d
-        return bic_from_terms(n1, n2, terms[0], terms[1], terms[2], self.lambdac)[0]
+        return bic_from_terms(n1, n2, terms[0], terms[1], terms[2], self.lambdac, p=self.dim)[0]
 
     # ---- merge mode ----------------------------------------------------------
     def _merge_step(self, feat, nxt, outf, segf):
@@ -444,6 +445,7 @@ class Detector(object):
                         owned.pop().close()
                     this_wav = line.audio
                     feat = load(line)
+                    self.dim = getattr(feat, 'dim', _abi.DIM)      # p of the BIC penalty (CD:97)
                     if loader is None:
                         owned.append(feat)
                 if self.method != 'm':

@@ -924,6 +924,8 @@ inline size_t cl_smem_bytes(int64_t n) {
 }
 
 cudaError_t cluster_small_configure();         // cluster_small.cuh
+cudaError_t cluster_set_dim(int d) { return set_dim_symbol(d); }
+
 cudaError_t cluster_configure() {
     cudaError_t e = cudaFuncSetAttribute(cl_merge_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;

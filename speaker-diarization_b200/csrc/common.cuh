@@ -176,6 +176,8 @@ static inline int check_metric(spkdiar_ctx* c, int metric) {
 }
 // per-translation-unit kernel attributes (dynamic shared memory sizes), called once by spkdiar_create
 cudaError_t gw_configure();
+cudaError_t gw_set_dim(int d);          // the feature dimension symbol of each translation unit (ldl.cuh: c_dim)
+cudaError_t cluster_set_dim(int d);
 cudaError_t cluster_configure();
 cudaError_t cluster_batch_configure();
 

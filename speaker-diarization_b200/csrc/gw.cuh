@@ -1062,6 +1062,8 @@ inline size_t gw_smem_bytes(bool kl2) {
            + sizeof(uint64_t) * GW_RING_STAGES + sizeof(long long) * 2 * GW_CHAIN_WARPS;
 }
 
+cudaError_t gw_set_dim(int d) { return set_dim_symbol(d); }
+
 cudaError_t gw_configure() {
     cudaError_t e = cudaFuncSetAttribute(gw_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)gw_smem_bytes(false));

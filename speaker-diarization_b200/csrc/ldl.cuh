@@ -21,6 +21,15 @@ constexpr int VS = 40;     // strip stride in doubles (>= D + 1, keeps 16-byte a
 
 constexpr int REC39 = Layout<39>::REC;
 
+// Feature files of fewer than 39 dimensions (the reference's loader takes the dimension from the file header,
+// spk-change-detection.py:37-41): frames are stored zero-padded to 39 columns, so every record, strip and
+// register tile keeps its one compiled shape, and the matrix that is factorised gets an IDENTITY block for the
+// padding: its diagonal is set to the value that makes S_kk = 1 there (form_matrix), so ln|S| and diag(S^-1) of
+// the real block come out unchanged.  c_dim is the real dimension (BIC penalty, "fewer frames than dimensions");
+// one value per device at a time, set by the upload (spkdiar.cu) in every translation unit.
+static __constant__ int c_dim = 39;
+static inline cudaError_t set_dim_symbol(int d) { return cudaMemcpyToSymbol(c_dim, &d, sizeof(int)); }
+
 // per-warp shared-memory scratch of the factorisation
 struct LdlScratch {
     double v[2][VS];       // column strips, double-buffered by step parity
@@ -151,6 +160,8 @@ __device__ __forceinline__ double form_matrix(double (&a)[Grid<D>::NSLOT],
     if (two) { ax = wx; ay = wy; c1 = wx / nx; c2 = wy / ny; }
     else c1 = 1.0 / (nx + ny);
     const int i = G::lane_i(lane), j = G::lane_j(lane);
+    const int dim = c_dim;
+    const double pad = two ? 1.0 : nx + ny - 1.0;            // M = (n - 1) S, or S itself for the GLR mix
     double u1[G::NRI], u2[G::NRI];
 #pragma unroll
     for (int ri = 0; ri < G::NRI; ++ri) {
@@ -170,6 +181,7 @@ __device__ __forceinline__ double form_matrix(double (&a)[Grid<D>::NSLOT],
             if (uy) m = fma(ay, y(q), m);
             m = fma(-u1[ri], sk0, m);
             if (two) m = fma(-u2[ri], sk1, m);
+            if (r == k && k >= dim) m = pad;                 // identity block of the zero-padded dimensions
             a[G::slot(kj, ri)] = m;
         }
     }
@@ -463,7 +475,7 @@ __device__ __forceinline__ double ldl_logdet_inv(double (&a)[Grid<D>::NSLOT], Ld
 // fp64 makes the reference see -inf / +inf.
 __device__ __forceinline__ double finish_logdet(double ln_m, double n, int d) {
     // no more frames than dimensions: the covariance is singular by construction (see ldl_logdet)
-    if (n > 1.0 && n <= (double)d) return -__longlong_as_double(0x7ff0000000000000LL);
+    if (n > 1.0 && n <= (double)c_dim) return -__longlong_as_double(0x7ff0000000000000LL);
     double v = ln_m - (double)d * log(n - 1.0);
     if (v < -744.4400719213812) v = -__longlong_as_double(0x7ff0000000000000LL);
     else if (v > 709.782712893384) v = __longlong_as_double(0x7ff0000000000000LL);

@@ -21,14 +21,9 @@ constexpr size_t SC_SMEM = SC_WARPS * sizeof(WarpScratch);     // dynamic shared
 // ---- distance formulas (fp64, reference operation order) ----------------------------
 // BIC, spk-change-detection.py:95-99 / spk-clustering.py:95-99:
 //   d = 0.5*N*ln|S| - 0.5*N1*ln|S1| - 0.5*N2*ln|S2|;  d -= lambda*0.5*(p+0.5*p*(p+1))*ln N
-__host__ __device__ inline double bic_penalty(double lambda, double N) {
-    const double p = (double)D39;
-    const double k = (lambda * 0.5) * (p + 0.5 * p * (p + 1.0));
-    return k * log(N);
-}
 // the penalty depends on N = N1 + N2 only: one log per window, not per candidate
 __device__ __forceinline__ double bic_pen(double lambda, double N) {
-    const double p = (double)D39;
+    const double p = (double)c_dim;                 // the dimension of the feature files (ldl.cuh)
     const double k = __dmul_rn(__dmul_rn(lambda, 0.5), __dadd_rn(p, __dmul_rn(__dmul_rn(0.5, p), p + 1.0)));
     return __dmul_rn(k, log(N));
 }

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <limits>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -125,6 +126,35 @@ int spkdiar_profile_read(const spkdiar_ctx* c, double* ms, int64_t* launches) {
 
 // ---- features + K1 ------------------------------------------------------------------------
 
+// One feature dimension per device at a time: the kernels read it from a __constant__ symbol (ldl.cuh: c_dim), which
+// is set here in every translation unit whenever the first handle of another dimension is made on a device that
+// has no live handle (every call of the library is synchronous, so nothing is in flight then).
+static std::mutex g_dim_mu;
+static int g_dev_dim[64];          // 0 = still the compiled default (39)
+static int g_dev_live[64];
+static int device_dim_acquire(spkdiar_ctx* c, int32_t dim) {
+    std::lock_guard<std::mutex> lock(g_dim_mu);
+    const int dev = c->device & 63;
+    const int cur = g_dev_dim[dev] ? g_dev_dim[dev] : D39;
+    if (cur != dim) {
+        if (g_dev_live[dev] > 0)
+            return set_err(c, SPKDIAR_E_UNSUPPORTED, "feature dimension %d while handles of dimension %d are alive on device %d: "
+                           "one dimension per device at a time", dim, cur, c->device);
+        cudaError_t e = set_dim_symbol(dim);
+        if (e == cudaSuccess) e = gw_set_dim(dim);
+        if (e == cudaSuccess) e = cluster_set_dim(dim);
+        if (e != cudaSuccess) return set_err(c, SPKDIAR_E_CUDA, "setting the feature dimension failed: %s", cudaGetErrorString(e));
+        g_dev_dim[dev] = dim;
+    }
+    g_dev_live[dev] += 1;
+    return SPKDIAR_OK;
+}
+static void device_dim_release(spkdiar_ctx* c) {
+    std::lock_guard<std::mutex> lock(g_dim_mu);
+    const int dev = c->device & 63;
+    if (g_dev_live[dev] > 0) g_dev_live[dev] -= 1;
+}
+
 // the arrays of the window statistics (K1): 6,560 B per frame + the block level
 static int stats_alloc(spkdiar_feat* f) {
     spkdiar_ctx* c = f->ctx;
@@ -146,24 +176,26 @@ static int feat_alloc(spkdiar_ctx* c, int64_t n, int32_t dim, spkdiar_feat** out
     if (!c || !out) return SPKDIAR_E_ARG;
     *out = nullptr;
     if (n < 0) return set_err(c, SPKDIAR_E_ARG, "negative frame count %lld", (long long)n);
-    if (dim != D39)
+    if (dim < 1 || dim > D39)
         return set_err(c, SPKDIAR_E_UNSUPPORTED,
-                       "feature dimension %d: the kernels are specialised for %d (fconfig.cfg) and there is no fallback",
-                       dim, D39);
+                       "feature dimension %d: the kernels handle 1..%d dimensions (fconfig.cfg has %d) and there is no fallback",
+                       dim, D39, D39);
     SPK_CUDA(c, cudaSetDevice(c->device));
+    if (int rc = device_dim_acquire(c, dim)) return rc;
     spkdiar_feat* f = new (std::nothrow) spkdiar_feat();
-    if (!f) return set_err(c, SPKDIAR_E_NOMEM, "host allocation failed");
+    if (!f) { device_dim_release(c); return set_err(c, SPKDIAR_E_NOMEM, "host allocation failed"); }
     f->ctx = c; f->n = n; f->dim = dim;
     f->ntiles = (n + K1_TILE - 1) / K1_TILE;
     f->nrec = nrec;
     cudaError_t e;
     if ((e = pool_alloc(c, (size_t)std::max(nrec, 1) * K1_XS * sizeof(double), (void**)&f->shift)) != cudaSuccess) {
+        device_dim_release(c);
         delete f;
         return set_err(c, e == cudaErrorMemoryAllocation ? SPKDIAR_E_NOMEM : SPKDIAR_E_CUDA,
                        "device allocation for %lld frames failed: %s", (long long)n, cudaGetErrorString(e));
     }
     if (with_stats) {
-        if (int rc = stats_alloc(f)) { pool_free(c, f->shift); delete f; return rc; }
+        if (int rc = stats_alloc(f)) { pool_free(c, f->shift); device_dim_release(c); delete f; return rc; }
     }
     *out = f;
     return SPKDIAR_OK;
@@ -271,7 +303,7 @@ static int upload_impl(spkdiar_ctx* c, const float* frames, int64_t n, int32_t d
     if (rc) return rc;
     spkdiar_feat* f = *out;
     float* dx = nullptr;
-    cudaError_t e = pool_alloc(c, (size_t)std::max<int64_t>(n, 1) * dim * sizeof(float), (void**)&dx);
+    cudaError_t e = pool_alloc(c, (size_t)std::max<int64_t>(n, 1) * D39 * sizeof(float), (void**)&dx);
     if (e != cudaSuccess) {
         spkdiar_features_free(f); *out = nullptr;
         return set_err(c, SPKDIAR_E_NOMEM, "device allocation for the frames failed: %s", cudaGetErrorString(e));
@@ -279,7 +311,13 @@ static int upload_impl(spkdiar_ctx* c, const float* frames, int64_t n, int32_t d
     f->x = dx; f->own_x = true;
     {
         Prof p(c, SPKDIAR_PROF_H2D);
-        if (n > 0) e = cudaMemcpyAsync(dx, frames, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+        if (n > 0 && dim == D39) e = cudaMemcpyAsync(dx, frames, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+        else if (n > 0) {                                   // fewer dimensions: rows zero-padded to 39 columns
+            e = cudaMemsetAsync(dx, 0, (size_t)n * D39 * sizeof(float), c->stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpy2DAsync(dx, D39 * sizeof(float), frames, (size_t)dim * sizeof(float), (size_t)dim * sizeof(float),
+                                      (size_t)n, cudaMemcpyHostToDevice, c->stream);
+        }
     }
     if (e != cudaSuccess) {
         spkdiar_features_free(f); *out = nullptr;
@@ -317,7 +355,7 @@ int spkdiar_features_upload_batch(spkdiar_ctx* c, const float* const* frames, co
     spkdiar_feat* f = *out;
     f->nrec = nrec; f->max_tiles = max_tiles;
     float* dx = nullptr;
-    cudaError_t e = pool_alloc(c, (size_t)rows * dim * sizeof(float), (void**)&dx);
+    cudaError_t e = pool_alloc(c, (size_t)rows * D39 * sizeof(float), (void**)&dx);
     if (e == cudaSuccess) { f->x = dx; f->own_x = true; e = pool_alloc(c, (size_t)nrec * sizeof(RecTab), &f->tab); }
     if (e != cudaSuccess) {
         spkdiar_features_free(f); *out = nullptr;
@@ -325,13 +363,15 @@ int spkdiar_features_upload_batch(spkdiar_ctx* c, const float* const* frames, co
     }
     {
         Prof p(c, SPKDIAR_PROF_H2D);
-        e = cudaMemsetAsync(dx, 0, (size_t)rows * dim * sizeof(float), c->stream);      // the padding rows
+        e = cudaMemsetAsync(dx, 0, (size_t)rows * D39 * sizeof(float), c->stream);      // the padding rows (and columns)
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(f->tab, tab.data(), (size_t)nrec * sizeof(RecTab), cudaMemcpyHostToDevice, c->stream);
         for (int32_t r = 0; r < nrec && e == cudaSuccess; ++r)
             if (n[r] > 0)
-                e = cudaMemcpyAsync(dx + tab[r].base * dim, frames[r], (size_t)n[r] * dim * sizeof(float),
-                                    cudaMemcpyHostToDevice, c->stream);
+                e = dim == D39 ? cudaMemcpyAsync(dx + tab[r].base * D39, frames[r], (size_t)n[r] * dim * sizeof(float),
+                                                 cudaMemcpyHostToDevice, c->stream)
+                               : cudaMemcpy2DAsync(dx + tab[r].base * D39, D39 * sizeof(float), frames[r], (size_t)dim * sizeof(float),
+                                                   (size_t)dim * sizeof(float), (size_t)n[r], cudaMemcpyHostToDevice, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);       // `tab` is a host temporary
     }
     if (e != cudaSuccess) {
@@ -347,7 +387,20 @@ int spkdiar_features_adopt(spkdiar_ctx* c, const float* dev_frames, int64_t n, i
     if (!c || !out || (!dev_frames && n > 0)) return c ? set_err(c, SPKDIAR_E_ARG, "null argument") : SPKDIAR_E_ARG;
     int rc = feat_alloc(c, n, dim, out);
     if (rc) return rc;
-    (*out)->x = dev_frames;
+    if (dim == D39) {
+        (*out)->x = dev_frames;
+    } else {                                                // fewer dimensions: an own, zero-padded copy
+        float* dx = nullptr;
+        cudaError_t e = pool_alloc(c, (size_t)std::max<int64_t>(n, 1) * D39 * sizeof(float), (void**)&dx);
+        if (e == cudaSuccess) { (*out)->x = dx; (*out)->own_x = true; e = cudaMemsetAsync(dx, 0, (size_t)std::max<int64_t>(n, 1) * D39 * sizeof(float), c->stream); }
+        if (e == cudaSuccess && n > 0)
+            e = cudaMemcpy2DAsync(dx, D39 * sizeof(float), dev_frames, (size_t)dim * sizeof(float), (size_t)dim * sizeof(float),
+                                  (size_t)n, cudaMemcpyDeviceToDevice, c->stream);
+        if (e != cudaSuccess) {
+            spkdiar_features_free(*out); *out = nullptr;
+            return set_err(c, SPKDIAR_E_CUDA, "padding the adopted frames failed: %s", cudaGetErrorString(e));
+        }
+    }
     rc = spkdiar_stats_build(*out);
     if (rc) { spkdiar_features_free(*out); *out = nullptr; }
     return rc;
@@ -364,6 +417,7 @@ int spkdiar_features_free(spkdiar_feat* f) {
     pool_free(f->ctx, f->tile);
     pool_free(f->ctx, f->tab);
     if (f->own_x) pool_free(f->ctx, f->x);
+    device_dim_release(f->ctx);
     delete f;
     return SPKDIAR_OK;
 }

@@ -200,7 +200,7 @@ def test_run_corpus_batched_equals_one_at_a_time(tmp_path):
 def test_argument_errors_of_the_batch_and_async_entry_points(ctx):
     rec = synth.make_recording(990, 3000, 2)
     with pytest.raises(_abi.SpkdiarError) as e:
-        ctx.upload_batch([np.zeros((10, 20), dtype=np.float32)])              # not 39-dimensional
+        ctx.upload_batch([np.zeros((10, 40), dtype=np.float32)])              # more than 39 dimensions
     assert e.value.code == -5
     with pytest.raises(_abi.SpkdiarError):
         ctx.upload_batch([])                                                  # an empty batch

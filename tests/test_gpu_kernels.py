@@ -191,7 +191,7 @@ def test_degenerate_windows_do_not_crash(ctx):
 
 def test_argument_errors(ctx, feat):
     with pytest.raises(_abi.SpkdiarError) as e:
-        ctx.upload(np.zeros((10, 13), dtype=np.float32))
+        ctx.upload(np.zeros((10, 40), dtype=np.float32))
     assert e.value.code == -5 and '39' in str(e.value)
     with pytest.raises(_abi.SpkdiarError):
         feat.score_windows([0], [10], [10 ** 9], _abi.BIC)
