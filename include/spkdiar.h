@@ -310,6 +310,19 @@ int  spkdiar_cluster_batch(spkdiar_feat* f, int32_t nprob, const int64_t* first,
                            const int64_t* seg_a, const int64_t* seg_b, int metric, double lambda,
                            double threshold, int32_t max_spk, int32_t variant,
                            spkdiar_merge* out, int64_t* nmerges, double* stats4);
+/* In-order clustering, spk_cluster_in of spk-clustering.py:136-175 / spk-clustering2.py:135-170, with the loop over
+ * the recipe lines ON THE DEVICE (one launch per recording instead of one scoring call per line): line l is the frame
+ * range [seg_a[l], seg_b[l]); it is scored against every speaker found so far (BIC or GLR of the speaker's frames and
+ * the segment's), joins the nearest one when that distance is <= threshold, else becomes a new speaker.  The speakers
+ * that exist before the first line (an earlier wav of the same recipe; nspk0 may be 0) are given as range sets:
+ * speaker s = ranges off0[s] .. off0[s + 1] of (a0, b0).  Out: dist[dist_first[l] .. dist_first[l + 1]) = the
+ * distances of line l to the speakers 0, 1, ... that existed then (none for the very first speaker), best[l] = the
+ * speaker joined or -1 for a new one.  The host replays the script's bookkeeping (statistics, -tt lines) from the
+ * distances.  A too small dist_cap returns SPKDIAR_E_CAPACITY (nlines * (nspk0 + nlines) always suffices). */
+int  spkdiar_cluster_inorder(spkdiar_feat* f, int32_t nspk0, const int64_t* off0, const int64_t* a0,
+                             const int64_t* b0, int64_t nlines, const int64_t* seg_a, const int64_t* seg_b,
+                             int metric, double lambda, double threshold,
+                             double* dist, int64_t dist_cap, int64_t* dist_first, int32_t* best);
 int  spkdiar_cluster_free(spkdiar_clus* c);
 /* test hook: copy the current pair matrix (nseg x nseg, row-major, entries of
  * dead rows / columns undefined) and the alive flags to the host */

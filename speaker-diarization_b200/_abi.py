@@ -39,7 +39,7 @@ SYMBOLS = (
     'spkdiar_ctx_exec',
     'spkdiar_replay_create', 'spkdiar_replay_free', 'spkdiar_replay_error', 'spkdiar_replay_info',
     'spkdiar_replay_chains', 'spkdiar_replay_segment', 'spkdiar_replay_turns', 'spkdiar_replay_cluster',
-    'spkdiar_replay_text', 'spkdiar_features_upload_frames',
+    'spkdiar_replay_text', 'spkdiar_features_upload_frames', 'spkdiar_cluster_inorder',
 )
 
 
@@ -135,6 +135,8 @@ def load_library(path=None):
         'spkdiar_gw_multi_where': (C.c_int, [vp, i32, C.POINTER(vp), C.POINTER(i32)]),
         'spkdiar_gw_multi_end': (C.c_int, [vp]),
         'spkdiar_ctx_exec': (C.c_int, [vp, vp, i32]),
+        'spkdiar_cluster_inorder': (C.c_int, [vp, i32, pi64, pi64, pi64, i64, pi64, pi64, C.c_int, dbl, dbl, pdbl, i64, pi64,
+                                              C.POINTER(C.c_int32)]),
         'spkdiar_replay_create': (C.c_int, [dbl, C.c_char_p, i64, C.POINTER(vp)]),
         'spkdiar_replay_free': (C.c_int, [vp]),
         'spkdiar_replay_error': (C.c_char_p, [vp]),
@@ -472,6 +474,38 @@ class Features(object):
             _p(d, C.c_double), _p(t, C.c_double) if terms else None))
         return (d, t) if terms else d
 
+    def cluster_inorder(self, speakers, seg_a, seg_b, metric, lambdac, threshold):
+        """``spk_cluster_in`` over the lines [seg_a[l], seg_b[l]) in ONE launch.  ``speakers``: the
+        range sets [[(a, b), ...], ...] of the speakers that exist before the first line.
+        -> (dist, first, best): the distances of line l to the speakers that existed then are
+        dist[first[l]:first[l + 1]], best[l] is the speaker joined or -1 for a new one."""
+        seg_a, seg_b = _i64(seg_a), _i64(seg_b)
+        nlines = seg_a.shape[0]
+        off = np.zeros(len(speakers) + 1, dtype=np.int64)
+        ra, rb = [], []
+        for s, ranges in enumerate(speakers):
+            for a, b in ranges:
+                ra.append(a)
+                rb.append(b)
+            off[s + 1] = len(ra)
+        ra, rb = _i64(ra), _i64(rb)
+        # line l sees at most len(speakers) + l speakers; usually far fewer: start small, grow on demand
+        full = nlines * len(speakers) + (nlines * (nlines - 1)) // 2 + 1
+        cap = min(full, max(nlines * (len(speakers) + 64), 1))
+        first = np.zeros(nlines + 1, dtype=np.int64)
+        best = np.zeros(max(nlines, 1), dtype=np.int32)
+        while True:
+            dist = np.empty(cap)
+            rc = self.ctx.lib.spkdiar_cluster_inorder(
+                self.h, len(speakers), _p(off, C.c_int64), _p(ra, C.c_int64), _p(rb, C.c_int64), nlines,
+                _p(seg_a, C.c_int64), _p(seg_b, C.c_int64), int(metric), float(lambdac), float(threshold),
+                _p(dist, C.c_double), cap, _p(first, C.c_int64), best.ctypes.data_as(C.POINTER(C.c_int32)))
+            if rc == -4 and cap < full:                 # SPKDIAR_E_CAPACITY
+                cap = full
+                continue
+            self.ctx._check(rc)
+            return dist[:int(first[nlines])], first, best[:nlines]
+
     def gw_run(self, seg_a, seg_b, rate, winsize, winstep, deltaws, threshold, lambdac, metric,
                max_groups=0, cap=None):
         """-> (window records [structured array], win_first [nchain + 1])"""
@@ -692,6 +726,10 @@ class FeatureView(object):
 
     def cluster(self, seg_a, seg_b, metric, lambdac=1.3):
         return self.pack.cluster(self._sh(seg_a), self._sh(seg_b), metric, lambdac)
+
+    def cluster_inorder(self, speakers, seg_a, seg_b, metric, lambdac, threshold):
+        sh = [[(a + self.off, b + self.off) for a, b in s] for s in speakers]
+        return self.pack.cluster_inorder(sh, self._sh(seg_a), self._sh(seg_b), metric, lambdac, threshold)
 
 
 class Clusters(object):

@@ -63,6 +63,7 @@ class Clusterer(object):
         self._own_ctx = ctx is None
         self.ctx = ctx if ctx is not None else _abi.Context(device)
         self._prefetch = {}
+        self._in_plan = {}             # line index -> (distances, decision) of the device-resident in-order loop
 
     def initial_segments(self, recipe, n):
         """The frame ranges of the initial clusters of a hierarchical run over ``recipe``
@@ -106,7 +107,27 @@ class Clusterer(object):
                 self.min_dist = d
 
     # ---- in-order clustering --------------------------------------------------
-    def _cluster_in(self, feat, line, outf, segf):
+    def _plan_in(self, feat, recipe, l):
+        """The device-resident loop over the lines l .. (last line of this wav): every distance and decision of
+        ``_cluster_in`` for them in ONE launch (``spkdiar_cluster_inorder``); the per-line code below then replays
+        the script's bookkeeping from the distances.  BIC and GLR; KL2 keeps one scoring call per line."""
+        rate = self.rate
+        m = l
+        while m < len(recipe) and recipe[m].audio == recipe[l].audio:
+            m += 1
+        segs = []
+        for line in recipe[l:m]:
+            if self.variant == 1:
+                segs.append(self._range((int(line.start * rate), int(line.end * rate)), feat.n))
+            else:
+                segs.append(self._range((line.start * rate, line.end * rate), feat.n))
+        dist, first, best = feat.cluster_inorder([self._ranges(s, feat.n) for s in self.speakers],
+                                                 [a for a, _ in segs], [b for _, b in segs],
+                                                 self.metric, self.lambdac, self.threshold)
+        for k in range(m - l):
+            self._in_plan[l + k] = (dist[int(first[k]):int(first[k + 1])], int(best[k]))
+
+    def _cluster_in(self, feat, line, outf, segf, index=None):
         """CL1:136-175 / CL2:135-170: the new segment against every speaker,
         one batched device call."""
         speakers = self.speakers
@@ -117,8 +138,14 @@ class Clusterer(object):
             start = line.start * self.rate
             end = line.end * self.rate
         seg = [self._range((start, end), feat.n)]
-        dist = feat.score_sets([self._ranges(s, feat.n) for s in speakers],
-                               [seg] * len(speakers), self.metric, self.lambdac)
+        plan = self._in_plan.pop(index, None) if index is not None else None
+        if plan is not None:
+            dist, device_best = plan                 # scored (and decided) by the device-resident loop
+            assert len(dist) == len(speakers), (len(dist), len(speakers))
+        else:
+            device_best = None
+            dist = feat.score_sets([self._ranges(s, feat.n) for s in speakers],
+                                   [seg] * len(speakers), self.metric, self.lambdac)
         mind = MAXINT
         best = None
         d = None
@@ -133,6 +160,9 @@ class Clusterer(object):
                 if d < mind:
                     mind = d
                     best = spk
+        if device_best is not None and (best if mind <= self.threshold else -1) != device_best:
+            raise RuntimeError('in-order clustering: host replay and device loop part at a line (%r against %r)'
+                               % (best if mind <= self.threshold else -1, device_best))
         if mind <= self.threshold:
             if self.variant == 1:                                  # CL1:164-167
                 if d > self.max_det_dist:
@@ -277,7 +307,10 @@ class Clusterer(object):
                 elif self.method == 'hi':
                     self.speakers.append([(line.start * rate, line.end * rate, l)])
                 else:
-                    self._cluster_in(feat, line, outf, segf)
+                    if self.engine == 'device' and self.metric != _abi.KL2 and l not in self._in_plan \
+                            and hasattr(feat, 'cluster_inorder'):
+                        self._plan_in(feat, recipe, l)
+                    self._cluster_in(feat, line, outf, segf, l)
             if self.method == 'hi':
                 self.log(p2line('Initial cluster with:', len(self.speakers), 'speakers'))
                 self._cluster_hi(feat, recipe, outf, segf)

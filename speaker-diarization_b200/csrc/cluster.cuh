@@ -932,12 +932,15 @@ inline size_t cl_smem_bytes(int64_t n) {
 }
 
 cudaError_t cluster_small_configure();         // cluster_small.cuh
+cudaError_t cluster_inorder_configure();       // cluster_inorder.cuh
 cudaError_t cluster_set_dim(int d) { return set_dim_symbol(d); }
 
 cudaError_t cluster_configure() {
     cudaError_t e = cudaFuncSetAttribute(cl_merge_loop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(cl_merge_loop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cluster_inorder_configure();
     if (e != cudaSuccess) return e;
     e = cluster_small_configure();
     if (e != cudaSuccess) return e;

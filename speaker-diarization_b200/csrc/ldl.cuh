@@ -181,7 +181,10 @@ __device__ __forceinline__ double form_matrix(double (&a)[Grid<D>::NSLOT],
             if (uy) m = fma(ay, y(q), m);
             m = fma(-u1[ri], sk0, m);
             if (two) m = fma(-u2[ri], sk1, m);
-            if (r == k && k >= dim) m = pad;                 // identity block of the zero-padded dimensions
+            // identity block of the zero-padded dimensions (only slots that can lie on the diagonal test anything:
+            // r - k = PR ri - PC kj + (i - j) with -PC < i - j < PR)
+            if (G::PC * kj - G::PR * ri > -G::PC && G::PC * kj - G::PR * ri < G::PR)
+                if (r == k && k >= dim) m = pad;
             a[G::slot(kj, ri)] = m;
         }
     }

@@ -12,8 +12,10 @@
 #include "cluster.cuh"
 #include "cluster_small.cuh"
 #include "cluster_batch.cuh"
+#include "cluster_inorder.cuh"
 
 using namespace spk;
 
 #include "abi_cluster.inc"
 #include "abi_batch.inc"
+#include "abi_inorder.inc"

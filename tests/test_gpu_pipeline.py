@@ -193,6 +193,33 @@ def test_device_merge_loop_scores_kl2(variant, ctx):
         feat.close()
 
 
+@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('dist,thr', [('BIC', 0.0), ('GLR', 900.0)])
+def test_device_resident_in_order_loop_equals_one_call_per_line(variant, dist, thr, ctx):
+    """spk_cluster_in (spk-clustering.py:136-175) with the line loop on the device (one launch per recording,
+    ``spkdiar_cluster_inorder``) against the host loop with one scoring call per line: the same -tt log (every
+    distance, bit for bit in its 12 printed digits), the same recipe, the same statistics - over two wavs, so that
+    the speakers found on the first are re-read as range sets on the second."""
+    rec = synth.make_recording(303, 15000, 4, turn_lo=2, turn_hi=6)
+    feat = ctx.upload(rec.frames)
+    half = len(rec.turns) // 2
+    recipe = [Line('/x.wav' if k < half else '/y.wav', 'a_%d' % (k + 1), a / 100.0, b / 100.0)
+              for k, (a, b, _) in enumerate(rec.turns)]
+    try:
+        res = []
+        for engine in ('device', 'host'):
+            log = []
+            cl = pcl.Clusterer(100, variant, 'in', dist, thr, 0, 1.3, tt=True, ctx=ctx, engine=engine,
+                               log=lambda *a: log.append(' '.join(map(str, a))))
+            out = io.StringIO()
+            cl.process_recipe(recipe, out, loader=lambda l: feat)
+            res.append((out.getvalue(), log, len(cl.speakers), cl.max_dist, cl.min_dist, cl.max_det_dist, cl.min_det_dist))
+        assert 1 < res[0][2] < len(recipe)
+        assert res[0] == res[1]
+    finally:
+        feat.close()
+
+
 def test_clustering_max_spk_forces_merges(tmp_path, ctx):
     rpath, feadir, rec = _case(tmp_path, 41, 7000, 4, kind='turns', turn_lo=2, turn_hi=5)
     for variant in (1, 2):
