@@ -323,6 +323,16 @@ int  spkdiar_cluster_inorder(spkdiar_feat* f, int32_t nspk0, const int64_t* off0
                              const int64_t* b0, int64_t nlines, const int64_t* seg_a, const int64_t* seg_b,
                              int metric, double lambda, double threshold,
                              double* dist, int64_t dist_cap, int64_t* dist_first, int32_t* best);
+/* Merge mode of the change detector, merge_rec of spk-change-detection.py:136-177 (driver loop 375-394), with the
+ * loop over the recipe lines of ONE wav on the device: step k scores the previous segment - line 0, or the run of
+ * lines merged so far, as ONE range from the first line's start to the last merged line's end - against line k + 1
+ * (BIC or GLR) and merges when the distance is below the threshold.  seg_a / seg_b: the clamped frame bounds
+ * int(start * rate), int(end * rate) of every line.  BIC with use_memo != 0 reproduces the reference's memo of the
+ * FIRST left term: *memo_c1 in (NaN = not set yet) and out.  Out per step: the three ln|S| terms
+ * (left, right, pooled / mixed), the distance and whether the lines were merged. */
+int  spkdiar_merge_chain(spkdiar_feat* f, int64_t nlines, const int64_t* seg_a, const int64_t* seg_b,
+                         int metric, double lambda, double threshold, int32_t use_memo, double* memo_c1,
+                         double* terms, double* dist, int32_t* merged);
 int  spkdiar_cluster_free(spkdiar_clus* c);
 /* test hook: copy the current pair matrix (nseg x nseg, row-major, entries of
  * dead rows / columns undefined) and the alive flags to the host */

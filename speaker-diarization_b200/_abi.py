@@ -40,6 +40,7 @@ SYMBOLS = (
     'spkdiar_replay_create', 'spkdiar_replay_free', 'spkdiar_replay_error', 'spkdiar_replay_info',
     'spkdiar_replay_chains', 'spkdiar_replay_segment', 'spkdiar_replay_turns', 'spkdiar_replay_cluster',
     'spkdiar_replay_text', 'spkdiar_features_upload_frames', 'spkdiar_cluster_inorder',
+    'spkdiar_merge_chain',
 )
 
 
@@ -137,6 +138,7 @@ def load_library(path=None):
         'spkdiar_ctx_exec': (C.c_int, [vp, vp, i32]),
         'spkdiar_cluster_inorder': (C.c_int, [vp, i32, pi64, pi64, pi64, i64, pi64, pi64, C.c_int, dbl, dbl, pdbl, i64, pi64,
                                               C.POINTER(C.c_int32)]),
+        'spkdiar_merge_chain': (C.c_int, [vp, i64, pi64, pi64, C.c_int, dbl, dbl, i32, pdbl, pdbl, pdbl, C.POINTER(C.c_int32)]),
         'spkdiar_replay_create': (C.c_int, [dbl, C.c_char_p, i64, C.POINTER(vp)]),
         'spkdiar_replay_free': (C.c_int, [vp]),
         'spkdiar_replay_error': (C.c_char_p, [vp]),
@@ -473,6 +475,22 @@ class Features(object):
             _p(o2, C.c_int64), _p(a2, C.c_int64), _p(b2, C.c_int64), int(metric), float(lambdac),
             _p(d, C.c_double), _p(t, C.c_double) if terms else None))
         return (d, t) if terms else d
+
+    def merge_chain(self, seg_a, seg_b, metric, lambdac, threshold, use_memo, memo_c1):
+        """``merge_rec`` over the lines of one wav in ONE launch.  ``memo_c1``: None or the memo of
+        the reference's first left BIC term.  -> (terms [n - 1][3], dist [n - 1], merged [n - 1],
+        memo_c1 after the chain)."""
+        seg_a, seg_b = _i64(seg_a), _i64(seg_b)
+        n = seg_a.shape[0]
+        terms = np.zeros((max(n - 1, 1), 3))
+        dist = np.zeros(max(n - 1, 1))
+        merged = np.zeros(max(n - 1, 1), dtype=np.int32)
+        memo = np.array([np.nan if memo_c1 is None else float(memo_c1)])
+        self.ctx._check(self.ctx.lib.spkdiar_merge_chain(
+            self.h, n, _p(seg_a, C.c_int64), _p(seg_b, C.c_int64), int(metric), float(lambdac), float(threshold),
+            1 if use_memo else 0, _p(memo, C.c_double), _p(terms, C.c_double), _p(dist, C.c_double),
+            merged.ctypes.data_as(C.POINTER(C.c_int32))))
+        return terms[:max(n - 1, 0)], dist[:max(n - 1, 0)], merged[:max(n - 1, 0)], (None if np.isnan(memo[0]) else memo[0])
 
     def cluster_inorder(self, speakers, seg_a, seg_b, metric, lambdac, threshold):
         """``spk_cluster_in`` over the lines [seg_a[l], seg_b[l]) in ONE launch.  ``speakers``: the

@@ -120,6 +120,8 @@ class Detector(object):
         self.ctx = ctx if ctx is not None else _abi.Context(device)
         self.windows_visited = 0
         self.dim = _abi.DIM            # of the feature file in use (set when it is loaded)
+        self._merge_plan = {}          # id(next line) -> step of the device-resident merge chain
+        self.merge_on_device = gw_on_device
         self._prefetch = {}
 
     def close(self):
@@ -388,6 +390,30 @@ class Detector(object):
         return bic_from_terms(n1, n2, terms[0], terms[1], terms[2], self.lambdac, p=self.dim)[0]
 
     # ---- merge mode ----------------------------------------------------------
+    def _plan_merge(self, feat, lines):
+        """The whole chain over the lines of one wav in ONE launch (``spkdiar_merge_chain``): per step the three
+        ln|S| terms, the distance and the decision.  ``_merge_step`` then replays the script's bookkeeping from
+        them and checks at every step that it stands where the device chain stood (same two frame ranges, same
+        decision); from a step where it does not - a tie between numpy's and the device's logarithm in the BIC
+        penalty - it goes on with one scoring call per line.  BIC and GLR; KL2 keeps the call per line."""
+        self._merge_plan.clear()
+        if self.metric == _abi.KL2 or not self.merge_on_device or len(lines) < 2 or not hasattr(feat, 'merge_chain'):
+            return
+        rate, n = self.rate, feat.n
+        a = [min(max(int(l.start * rate), 0), n) for l in lines]
+        b = [min(max(int(l.end * rate), 0), n) for l in lines]
+        terms, dist, merged, _ = feat.merge_chain(a, b, self.metric, self.lambdac, self.threshold,
+                                                  self.bic_cache == 'reference', self.memo_c1)
+        pa, pb = a[0], b[0]
+        for k in range(len(lines) - 1):
+            r1 = (pa, max(pa, pb))
+            r2 = (a[k + 1], max(a[k + 1], b[k + 1]))
+            self._merge_plan[id(lines[k + 1])] = ((r1, r2), terms[k], dist[k], bool(merged[k]))
+            if merged[k]:
+                pb = b[k + 1]
+            else:
+                pa, pb = a[k + 1], b[k + 1]
+
     def _merge_step(self, feat, nxt, outf, segf):
         """CD:136-177: previous (possibly already merged) segment against the
         next one; whole-file frame indices, float bounds truncated."""
@@ -402,7 +428,19 @@ class Detector(object):
         r2 = (clamp(nxt.start * rate), clamp(nxt.end * rate))
         r1 = (r1[0], max(r1))
         r2 = (r2[0], max(r2))
-        if self.metric == _abi.BIC:
+        plan = self._merge_plan.pop(id(nxt), None)
+        if plan is not None and plan[0] != (r1, r2):
+            plan = None                                  # the device chain stands elsewhere: its steps no longer apply
+            self._merge_plan.clear()
+        if plan is not None:
+            # scored (and decided) by the device-resident chain, spkdiar_merge_chain
+            if self.metric == _abi.BIC:
+                d = self._bic_memo(r1[1] - r1[0], r2[1] - r2[0], plan[1])
+            else:
+                d = plan[2]
+            if bool(d < self.threshold and not _is_inf(d)) != plan[3]:
+                self._merge_plan.clear()                 # (a rounding tie between the host's and the device's log)
+        elif self.metric == _abi.BIC:
             _, terms = feat.score_sets([[r1]], [[r2]], self.metric, self.lambdac, terms=True)
             d = self._bic_memo(r1[1] - r1[0], r2[1] - r2[0], terms[0])
         else:
@@ -468,6 +506,10 @@ class Detector(object):
                         if wav_start:
                             wav_start = False
                             self.prev = line
+                            m = l
+                            while m < len(recipe) and recipe[m].audio == this_wav:
+                                m += 1
+                            self._plan_merge(feat, recipe[l:m])
                         self._merge_step(feat, recipe[l + 1], outf, segf)
                     else:
                         p = self.prev

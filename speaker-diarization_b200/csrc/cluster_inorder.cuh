@@ -121,8 +121,79 @@ static __global__ void __launch_bounds__(CL_THREADS, 1) cl_inorder_kernel(const 
     }
 }
 
+cudaError_t cd_merge_chain_configure();
 cudaError_t cluster_inorder_configure() {
-    return cudaFuncSetAttribute(cl_inorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_inorder_smem_bytes());
+    cudaError_t e = cudaFuncSetAttribute(cl_inorder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_inorder_smem_bytes());
+    return e != cudaSuccess ? e : cd_merge_chain_configure();
+}
+
+}  // namespace spk
+
+// ---- merge mode of the change detector (spk-change-detection.py:136-177, 375-394) on the device ----
+// `-m m` walks the recipe lines of a wav: the previous segment (possibly already merged with its predecessors) is
+// scored against the next line; below the threshold the two are merged (the previous one now ends where the next
+// ends), else the previous one is written and the next takes its place.  One dependent decision per line; here one
+// CTA does the whole chain (three warps: left, right and pooled / mixed term of a step; thread 0 decides).
+// BIC goes through the reference's memo of the first left term (the mutable default of `bic`):
+// c1_memo in/out, NaN = not set yet, `use_memo` = --bic-cache reference.
+namespace spk {
+
+struct MgDev {
+    Stats st;
+    int64_t nlines;
+    const int64_t* la; const int64_t* lb;      // [nlines] clamped frame bounds of every line (start, end)
+    int metric; double lambda; double threshold; int use_memo;
+    double* terms;                             // [nlines - 1][3] left, right, pooled / mixed ln|S| of step k
+    double* dist;                              // [nlines - 1]
+    int32_t* merged;                           // [nlines - 1] 1: line k + 1 was merged into the previous segment
+    double* memo;                              // [1] c1 of the reference's memo (NaN: empty)
+};
+
+static __global__ void __launch_bounds__(CL_THREADS, 1) cd_merge_chain_kernel(const MgDev g) {
+    extern __shared__ __align__(16) unsigned char in_smem[];
+    WarpScratch* ws = reinterpret_cast<WarpScratch*>(in_smem);
+    __shared__ double s_t[3];
+    __shared__ long long s_pa, s_pb;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { s_pa = g.la[0]; s_pb = g.lb[0]; }
+    __syncthreads();
+    double memo = *g.memo;
+    for (int64_t k = 0; k + 1 < g.nlines; ++k) {
+        const int64_t a1 = s_pa, b1 = s_pb > s_pa ? s_pb : s_pa;
+        const int64_t a2 = g.la[k + 1], b2 = g.lb[k + 1] > a2 ? g.lb[k + 1] : a2;
+        if (warp < 3) {
+            const WinSrc X(g.st, a1, b1, REC), Y(g.st, a2, b2, REC);
+            const double v = logdet_term(warp, g.metric, X, Y, ws[warp], lane);
+            if (lane == 0) s_t[warp] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double N1 = (double)(b1 - a1), N2 = (double)(b2 - a2);
+            double d;
+            if (g.metric == SPKDIAR_BIC) {
+                double c1 = __dmul_rn(__dmul_rn(0.5, N1), s_t[0]);
+                if (g.use_memo) { if (memo != memo) memo = c1; else c1 = memo; }
+                const double N = N1 + N2;
+                const double t0 = __dmul_rn(__dmul_rn(0.5, N), s_t[2]);
+                const double t2 = __dmul_rn(__dmul_rn(0.5, N2), s_t[1]);
+                d = __dsub_rn(__dsub_rn(__dsub_rn(t0, c1), t2), bic_pen(g.lambda, N));
+            } else {
+                d = glr_combine(N1, N2, s_t[0], s_t[1], s_t[2]);
+            }
+            const bool merge = d < g.threshold && d != d_inf() && d != -d_inf();       // CD:163-166
+            g.terms[3 * k] = s_t[0]; g.terms[3 * k + 1] = s_t[1]; g.terms[3 * k + 2] = s_t[2];
+            g.dist[k] = d;
+            g.merged[k] = merge ? 1 : 0;
+            if (merge) s_pb = g.lb[k + 1];                                              // prev now ends where next ends
+            else { s_pa = g.la[k + 1]; s_pb = g.lb[k + 1]; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *g.memo = memo;
+}
+
+cudaError_t cd_merge_chain_configure() {
+    return cudaFuncSetAttribute(cd_merge_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cl_inorder_smem_bytes());
 }
 
 }  // namespace spk

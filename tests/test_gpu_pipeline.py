@@ -220,6 +220,38 @@ def test_device_resident_in_order_loop_equals_one_call_per_line(variant, dist, t
         feat.close()
 
 
+@pytest.mark.parametrize('dist,thr,cache', [('BIC', 0.0, 'reference'), ('BIC', 0.0, 'correct'), ('GLR', 900.0, 'reference')])
+def test_device_resident_merge_chain_equals_one_call_per_line(dist, thr, cache, ctx):
+    """merge_rec (spk-change-detection.py:136-177) with the line loop on the device (``spkdiar_merge_chain``)
+    against the host loop with one scoring call per line: same -tt log, same recipe, same statistics - two wavs, the
+    reference's first-left-term memo carried from the first chain into the second."""
+    rec = synth.make_recording(304, 15000, 3, turn_lo=2, turn_hi=5)
+    feat = ctx.upload(rec.frames)
+    pieces = []                                        # every turn cut in two: neighbours of one speaker do merge
+    for a, b, _ in rec.turns:
+        mid = (a + b) // 2
+        pieces += [(a, mid), (mid, b)]
+    half = len(pieces) // 2
+    recipe = [Line('/x.wav' if k < half else '/y.wav', 'a_%d' % (k + 1), a / 100.0, b / 100.0)
+              for k, (a, b) in enumerate(pieces)]
+    try:
+        res = []
+        for on_device in (True, False):
+            log = []
+            det = pcd.Detector(100, 'm', dist, 1.0, 3.0, 0.1, thr, 1.3, tt=True, bic_cache=cache, ctx=ctx,
+                               gw_on_device=on_device, log=lambda *a: log.append(' '.join(map(str, a))))
+            out = io.StringIO()
+            det.detect_changes(recipe, out, loader=lambda l: feat)
+            st = det.stats
+            res.append((out.getvalue(), log, det.windows_visited, st.total_segments, st.total_dist, st.max_dist, st.min_dist))
+        assert res[0][2] == len(recipe) - 2
+        if cache == 'correct' or dist == 'GLR':
+            assert 0 < res[0][3] < len(recipe)          # (the reference's memo makes BIC meaningless: SURVEY.md Q2)
+        assert res[0] == res[1]
+    finally:
+        feat.close()
+
+
 def test_clustering_max_spk_forces_merges(tmp_path, ctx):
     rpath, feadir, rec = _case(tmp_path, 41, 7000, 4, kind='turns', turn_lo=2, turn_hi=5)
     for variant in (1, 2):
