@@ -485,60 +485,4 @@ __device__ __forceinline__ double finish_logdet(double ln_m, double n, int d) {
     return v;
 }
 
-// ---- diag(M^-1) from the stored factor (KL2 only) --------------------
-// X = L^-1 is unit lower triangular; column j of X is owned by lane l as the
-// pair (j = l, rows l..D-1) and (j = D-1-l, rows D-1-l..D-1).
-//   diag(M^-1)_j = sum_{r >= j} X_rj^2 / p_r
-// Returns the value for column `lane` in ga and for column D-1-lane in gb.
-template <int D>
-struct InvCols { static constexpr int NL = (D + 1) / 2; };     // lanes that own column pairs of L^-1
-template <int D, int R>
-struct InvRow {
-    using L = InvCols<D>;
-    static constexpr int HB = D - L::NL;
-    static __device__ __forceinline__ void run(const double* Lsm, int lane, double (&xa)[D], double (&xb)[L::NL]) {
-        const double* row = Lsm + (R * (R - 1)) / 2;
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-            if (k & 1) a1 = fma(row[k], xa[k], a1); else a0 = fma(row[k], xa[k], a0);
-        }
-        // rows above the column's own diagonal stay 0; the diagonal stays 1
-        if (R > lane) xa[R] = -(a0 + a1);
-        if (R > HB) {
-            double b0 = 0.0, b1 = 0.0;
-#pragma unroll
-            for (int k = HB; k < R; ++k) {
-                if (k & 1) b1 = fma(row[k], xb[k - HB], b1); else b0 = fma(row[k], xb[k - HB], b0);
-            }
-            if (R > D - 1 - lane) xb[R > HB ? R - HB : 0] = -(b0 + b1);
-        }
-        InvRow<D, R + 1>::run(Lsm, lane, xa, xb);
-    }
-};
-template <int D>
-struct InvRow<D, D> {
-    using L = InvCols<D>;
-    static __device__ __forceinline__ void run(const double*, int, double (&)[D], double (&)[L::NL]) {}
-};
-
-template <int D>
-__device__ __forceinline__ void inv_diag(const double* Lsm, const double* pinv, int lane,
-                                         double& ga, double& gb) {
-    using L = InvCols<D>;
-    constexpr int HB = D - L::NL;          // first row of the short columns (19 for D = 39)
-    double xa[D];                          // column `lane`, indexed by row
-    double xb[L::NL];                      // column D-1-lane, rows HB..D-1 -> index r - HB
-#pragma unroll
-    for (int r = 0; r < D; ++r) xa[r] = (r == lane) ? 1.0 : 0.0;
-#pragma unroll
-    for (int r = HB; r < D; ++r) xb[r - HB] = (r == D - 1 - lane) ? 1.0 : 0.0;
-    InvRow<D, 1>::run(Lsm, lane, xa, xb);
-    ga = 0.0; gb = 0.0;
-#pragma unroll
-    for (int r = 0; r < D; ++r) ga = fma(xa[r] * xa[r], pinv[r], ga);
-#pragma unroll
-    for (int r = HB; r < D; ++r) gb = fma(xb[r - HB] * xb[r - HB], pinv[r], gb);
-}
-
 }  // namespace spk
