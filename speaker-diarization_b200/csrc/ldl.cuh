@@ -161,7 +161,6 @@ __device__ __forceinline__ double form_matrix(double (&a)[Grid<D>::NSLOT],
     else c1 = 1.0 / (nx + ny);
     const int i = G::lane_i(lane), j = G::lane_j(lane);
     const int dim = c_dim;
-    const double pad = two ? 1.0 : nx + ny - 1.0;            // M = (n - 1) S, or S itself for the GLR mix
     double u1[G::NRI], u2[G::NRI];
 #pragma unroll
     for (int ri = 0; ri < G::NRI; ++ri) {
@@ -181,11 +180,23 @@ __device__ __forceinline__ double form_matrix(double (&a)[Grid<D>::NSLOT],
             if (uy) m = fma(ay, y(q), m);
             m = fma(-u1[ri], sk0, m);
             if (two) m = fma(-u2[ri], sk1, m);
-            // identity block of the zero-padded dimensions (only slots that can lie on the diagonal test anything:
-            // r - k = PR ri - PC kj + (i - j) with -PC < i - j < PR)
-            if (G::PC * kj - G::PR * ri > -G::PC && G::PC * kj - G::PR * ri < G::PR)
-                if (r == k && k >= dim) m = pad;
             a[G::slot(kj, ri)] = m;
+        }
+    }
+    // identity block of the zero-padded dimensions of a file with fewer than D of them (a warp-uniform branch that
+    // files of D dimensions skip; only slots that can lie on the diagonal test anything: r - k = PR ri - PC kj +
+    // (i - j) with -PC < i - j < PR)
+    if (dim < D) {
+        const double pad = two ? 1.0 : nx + ny - 1.0;        // M = (n - 1) S, or S itself for the GLR mix
+#pragma unroll
+        for (int kj = 0; kj < G::NKJ; ++kj) {
+#pragma unroll
+            for (int ri = G::ri_first(kj); ri < G::NRI; ++ri) {
+                if (G::PC * kj - G::PR * ri > -G::PC && G::PC * kj - G::PR * ri < G::PR) {
+                    const int r = i + G::PR * ri, k = j + G::PC * kj;
+                    if (r == k && k >= dim) a[G::slot(kj, ri)] = pad;
+                }
+            }
         }
     }
     __syncwarp();
