@@ -47,7 +47,11 @@ extern "C" {
 #define SPKDIAR_BIC 1
 #define SPKDIAR_KL2 2
 
-/* the feature dimension the kernels are specialised for (fconfig.cfg:78-83) */
+/* the feature dimension the kernels are compiled for (fconfig.cfg:78-83).  Feature files of 1..SPKDIAR_DIM
+ * dimensions are accepted (the reference's loader takes the dimension from the file header,
+ * spk-change-detection.py:37-41): the library keeps such frames zero-padded to SPKDIAR_DIM columns and treats
+ * the padding as an identity block, so every distance is that of the file's own dimensions; one dimension per
+ * device at a time (handles of another dimension are refused while any is alive). */
 #define SPKDIAR_DIM 39
 /* doubles per sufficient-statistics record: 780 packed second moments,
  * 39 first moments, 1 frame count */
