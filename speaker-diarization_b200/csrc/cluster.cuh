@@ -524,15 +524,9 @@ __device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, i
         else { has = mine_pair(k); term = 2; kk = has ? k : a; }
         if (round > 0 && k >= n) break;
         double t = 0.0;
-        // what lane 0 needs next to ln|S_pooled|: asked for BEFORE the factorisation, which hides the round trips
         double N2 = 0.0, ldk = 0.0, vold = 0.0;
         int32_t cmin = -1;
-        if (has && term == 2 && lane == 0) {
-            N2 = __ldcg(g.rec + kk * REC + L39::CNT);
-            if (!kl2) ldk = __ldcg(g.ld + kk);
-            cmin = __ldcg(g.rowmin_c + kk);
-            if (g.variant == 1) vold = __ldcg(g.rowmin_v + kk);
-        }
+        if (kl2 && has && term == 2 && lane == 0) N2 = __ldcg(g.rec + kk * REC + L39::CNT);
         double dk = 0.0;
         if constexpr (KL2) {
             if (has) {
@@ -551,6 +545,12 @@ __device__ __forceinline__ double cl_phase_apply(const ClDev& g, long long nm, i
             ld_ab = sm.shd[0];
         }
         if (has && term == 2 && lane == 0) {
+            // (requested AFTER the factorisation: held across it, these seven registers cost more in spills inside
+            // it than the round trips they would hide - measured 217 k against 187 k cycles per merge at 23,881
+            // clusters; keeping the per-warp results in shared memory instead of registers was slower again, 200 k)
+            if (!kl2) { N2 = __ldcg(g.rec + kk * REC + L39::CNT); ldk = __ldcg(g.ld + kk); }
+            cmin = __ldcg(g.rowmin_c + kk);
+            if (g.variant == 1) vold = __ldcg(g.rowmin_v + kk);
             const double d = kl2 ? dk : (g.metric == SPKDIAR_BIC ? bic_combine(N1, N2, ld_ab, ldk, t, g.lambda)
                                                                  : glr_combine(N1, N2, ld_ab, ldk, t));
             g.M[a * n + kk] = d;                                            // row a
