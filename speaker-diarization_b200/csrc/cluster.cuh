@@ -182,8 +182,12 @@ cl_fill_pairs(const double* rec, const double* __restrict__ ld, int64_t n, int m
         }
         const SmemSrc X{w.rec[0]};
         const RecSrc Y{rec + j * REC};
-        const double d = cl_pair_distance(metric, lambda, X, Y, ld[i], ld[j], w, lane);
+        // (ln|S_i|, ln|S_j| are read AFTER the factorisation: nothing that can wait is held across it)
+        const double t = logdet_term(2, metric, X, Y, w, lane);
         if (lane == 0) {
+            const double N1 = X(L39::CNT), N2 = Y(L39::CNT);
+            const double d = metric == SPKDIAR_BIC ? bic_combine(N1, N2, ld[i], ld[j], t, lambda)
+                                                   : glr_combine(N1, N2, ld[i], ld[j], t);
             M[i * n + j] = d;
             if (variant == 1) { M[j * n + i] = d; track.see(d); }
         }
